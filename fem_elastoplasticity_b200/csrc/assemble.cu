@@ -1,0 +1,324 @@
+// K3/K4/K6: stiffness assembly, strain and internal force.
+//
+// Assembly is a deterministic GATHER, not a scatter: one thread owns one node (two CSR rows), walks
+// the node's incident elements in ascending element order (sliced-ELL incidence list, coalesced) and
+// accumulates every entry of its two rows in exactly the order scipy's csr_matmat uses for
+// K = B^T D B (Plasticity2D_DP/pythonFEM.py:595): ascending (element, quadrature point, strain row).
+// No atomics, no zero-fill pass, every K value is written exactly once; with -fmad=false the values
+// are bit-identical to the reference.  The 2*deg*2 row accumulators live in warp-private shared
+// memory laid out [entry][lane] (conflict-free), and are written out as contiguous CSR row pairs.
+#include "common.cuh"
+
+struct AsmArgs {
+  int64_t n_n, n_e, n_int, n_slices, sell_entries;
+  const int32_t* nbr_ptr;
+  const int64_t* slice_ptr;
+  const uint32_t* inc_key;
+  const uint32_t* inc_meta;
+  const double* dphi1;
+  const double* dphi2;
+  const double* weight;
+  // mode inputs
+  const double* shear;  // MODE 0, 2
+  const double* bulk;   // MODE 0, 2
+  const double* DS;     // MODE 1, 2   [9][n_int]
+  const double* Kel;    // MODE 2
+  const double* S;      // FORCE       [>=3][n_int]
+  double* K_vals;
+  double* F;
+  int acc_rows;         // 4 * max_degree
+  double dev2[9];       // 2*Dev (column-major) formed as numpy forms it (:579-582)
+  double vol[9];
+};
+
+constexpr int ACC_LD = 33;  // padded leading dimension: bank = (entry + lane) mod 16 for doubles
+
+enum { MODE_ELASTIC = 0, MODE_TANGENT = 1, MODE_TANGENT_REF = 2, MODE_FORCE_ONLY = 3 };
+
+template <int NP, int NQ, int MODE, bool FORCE>
+__global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
+  extern __shared__ double smem[];
+  constexpr int MW = (NP + 1 + 3) / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slice >= A.n_slices) return;  // warp-uniform; only warp-level synchronisation below
+  double* acc = smem + (size_t)warp * A.acc_rows * ACC_LD;
+  const int64_t a = slice * 32 + lane;
+  int deg = 0, base = 0;
+  if (a < A.n_n) {
+    const int nb = A.nbr_ptr[a];
+    deg = A.nbr_ptr[a + 1] - nb;
+    base = 4 * nb;
+  }
+  if (MODE != MODE_FORCE_ONLY)
+    for (int k = 0; k < 4 * deg; ++k) acc[k * ACC_LD + lane] = 0.0;
+  const int64_t sbase = A.slice_ptr[slice];
+  const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
+  const int64_t n_int = A.n_int;
+  double f0 = 0.0, f1 = 0.0;
+  for (int i = 0; i < width; ++i) {
+    const int64_t at = sbase + (int64_t)i * 32 + lane;
+    const uint32_t key = __ldcs(A.inc_key + at);
+    if (key == FEM_INVALID_KEY) continue;
+    const int64_t e = key >> 3;
+    const int la = key & 7;
+    uint32_t meta[MW];
+#pragma unroll
+    for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      const int64_t g = e * NQ + q;
+      const double w = A.weight[g];
+      double d1[NP], d2[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        d1[p] = A.dphi1[(int64_t)p * n_int + g];
+        d2[p] = A.dphi2[(int64_t)p * n_int + g];
+      }
+      double d1a = d1[0], d2a = d2[0];
+#pragma unroll
+      for (int p = 1; p < NP; ++p)
+        if (p == la) {
+          d1a = d1[p];
+          d2a = d2[p];
+        }
+      if (FORCE) {  // F = B^T (w*s), csc_matvec order: strain rows 3g, 3g+1, 3g+2   (:1058)
+        const double ws0 = w * A.S[g], ws1 = w * A.S[n_int + g], ws2 = w * A.S[2 * n_int + g];
+        f0 = (f0 + d1a * ws0) + d2a * ws2;
+        f1 = (f1 + d2a * ws1) + d1a * ws2;
+      }
+      if (MODE == MODE_FORCE_ONLY) continue;
+      double D[9];  // D[r + 3c]
+      if (MODE == MODE_ELASTIC) {            // vd = (2*dev*G + vol*K) * (1*w)        (:582,591)
+        const double G = A.shear[g], Kb = A.bulk[g];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) D[k] = (A.dev2[k] * G + A.vol[k] * Kb) * w;
+      } else if (MODE == MODE_TANGENT) {     // vD = w * ds                            (:1047)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g];
+      } else {                               // D_p - D_elast                          (:1050)
+        const double G = A.shear[g], Kb = A.bulk[g];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g] - (A.dev2[k] * G + A.vol[k] * Kb) * w;
+      }
+      // t = (B^T D)[dof, 3g + c]; B columns of node la: x-dof (d1,0,d2), y-dof (0,d2,d1)
+      double tx[3], ty[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tx[c] = d1a * D[3 * c] + d2a * D[2 + 3 * c];
+        ty[c] = d2a * D[1 + 3 * c] + d1a * D[2 + 3 * c];
+      }
+#pragma unroll
+      for (int lb = 0; lb < NP; ++lb) {
+        const int byte = lb + 1;
+        const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
+        double* r0 = acc + (2 * slot) * ACC_LD + lane;
+        double* r1 = acc + (2 * deg + 2 * slot) * ACC_LD + lane;
+        const double b1 = d1[lb], b2 = d2[lb];
+        r0[0] = (r0[0] + tx[0] * b1) + tx[2] * b2;            // K[2a  , 2b  ]
+        r0[ACC_LD] = (r0[ACC_LD] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
+        r1[0] = (r1[0] + ty[0] * b1) + ty[2] * b2;            // K[2a+1, 2b  ]
+        r1[ACC_LD] = (r1[ACC_LD] + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+      }
+    }
+  }
+  if (FORCE && a < A.n_n) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+  if (MODE == MODE_FORCE_ONLY) return;
+  __syncwarp();
+  // write-out: the two rows of node t are 4*deg_t contiguous CSR values starting at base_t
+  for (int t = 0; t < 32; ++t) {
+    const int n4 = 4 * __shfl_sync(0xffffffffu, deg, t);
+    const int bt = __shfl_sync(0xffffffffu, base, t);
+    for (int l = lane; l < n4; l += 32) {
+      double v = acc[l * ACC_LD + t];
+      if (MODE == MODE_TANGENT_REF) v = A.Kel[bt + l] + v;  // csr_plus_csr: K_elast + correction
+      __stcs(A.K_vals + bt + l, v);
+    }
+  }
+}
+
+// host-formed constants, exactly as numpy does at Plasticity2D_DP/pythonFEM.py:579-582
+static void elastic_coeffs(double* dev2, double* vol) {
+  const double iota[3] = {1.0, 1.0, 0.0};
+  const double diag[3] = {1.0, 1.0, 0.5};
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r) {
+      const volatile double v = iota[r] * iota[c];
+      const volatile double third = v / 3.0;
+      const volatile double dev = (r == c ? diag[r] : 0.0) - third;
+      dev2[r + 3 * c] = 2.0 * dev;
+      vol[r + 3 * c] = v;
+    }
+}
+
+struct DmatCoef { double dev2[9], vol[9]; };
+__global__ void elastic_dmat_kernel(int64_t n_int, DmatCoef k, const double* __restrict__ shear, const double* __restrict__ bulk,
+                                    const double* __restrict__ weight, double* __restrict__ vd) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_int; g += (int64_t)gridDim.x * blockDim.x) {
+    const double G = shear[g], Kb = bulk[g], w = weight[g];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) vd[(int64_t)q * n_int + g] = (k.dev2[q] * G + k.vol[q] * Kb) * w;
+  }
+}
+
+extern "C" int fem_elastic_dmat(const fem_plan* P, const double* shear, const double* bulk, double* vd, fem_stream stream) {
+  FEM_REQUIRE(P && shear && bulk && vd, "null pointer");
+  DmatCoef k;
+  elastic_coeffs(k.dev2, k.vol);
+  int64_t b = (P->n_int + 255) / 256;
+  if (b > (int64_t)P->sm_count * 64) b = (int64_t)P->sm_count * 64;
+  elastic_dmat_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(P->n_int, k, shear, bulk, P->weight, vd);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+template <int MODE, bool FORCE>
+static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
+  const int warps = (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= 4) ? g_fem_tuning.assemble_warps : 4;
+  int acc_rows = (MODE == MODE_FORCE_ONLY) ? 0 : 4 * P->max_degree;
+  A.acc_rows = acc_rows;
+  size_t smem = (size_t)warps * acc_rows * ACC_LD * sizeof(double);
+  int threads = warps * 32;
+  if (smem > 200 * 1024) {  // very high valence: one warp per block
+    threads = 32;
+    smem = (size_t)acc_rows * ACC_LD * sizeof(double);
+    if (smem > 227 * 1024) {
+      fem_set_error("node degree %d needs %zu B of shared memory", P->max_degree, smem);
+      return FEM_ERR_UNSUPPORTED;
+    }
+  }
+  const unsigned blocks = (unsigned)fem_div_up(P->n_slices, threads / 32);
+#define LAUNCH(NP, NQ)                                                                                          \
+  do {                                                                                                          \
+    auto kern = assemble_rows_kernel<NP, NQ, MODE, FORCE>;                                                      \
+    if (smem > 48 * 1024) FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<blocks, threads, smem, st>>>(A);                                                                     \
+  } while (0)
+  if (P->n_p == 3 && P->n_q == 1) LAUNCH(3, 1);
+  else if (P->n_p == 6 && P->n_q == 7) LAUNCH(6, 7);
+  else if (P->n_p == 4 && P->n_q == 4) LAUNCH(4, 4);
+  else if (P->n_p == 8 && P->n_q == 9) LAUNCH(8, 9);
+  else {
+    fem_set_error("unsupported element n_p=%d n_q=%d", P->n_p, P->n_q);
+    return FEM_ERR_UNSUPPORTED;
+  }
+#undef LAUNCH
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+static void fill_args(const fem_plan* P, AsmArgs& A) {
+  memset(&A, 0, sizeof(A));
+  A.n_n = P->n_n; A.n_e = P->n_e; A.n_int = P->n_int; A.n_slices = P->n_slices; A.sell_entries = P->sell_entries;
+  A.nbr_ptr = P->nbr_ptr; A.slice_ptr = P->slice_ptr; A.inc_key = P->inc_key; A.inc_meta = P->inc_meta;
+  A.dphi1 = P->dphi1; A.dphi2 = P->dphi2; A.weight = P->weight;
+  elastic_coeffs(A.dev2, A.vol);
+}
+
+extern "C" int fem_assemble_elastic(const fem_plan* P, const double* shear, const double* bulk, double* K_vals,
+                                    fem_stream stream) {
+  FEM_REQUIRE(P && shear && bulk && K_vals, "null pointer");
+  AsmArgs A;
+  fill_args(P, A);
+  A.shear = shear; A.bulk = bulk; A.K_vals = K_vals;
+  return launch_assemble<MODE_ELASTIC, false>(P, A, (cudaStream_t)stream);
+}
+
+extern "C" int fem_assemble_tangent(const fem_plan* P, const double* DS, double* K_vals, fem_stream stream) {
+  FEM_REQUIRE(P && DS && K_vals, "null pointer");
+  AsmArgs A;
+  fill_args(P, A);
+  A.DS = DS; A.K_vals = K_vals;
+  return launch_assemble<MODE_TANGENT, false>(P, A, (cudaStream_t)stream);
+}
+
+extern "C" int fem_assemble_tangent_ref(const fem_plan* P, const double* DS, const double* shear, const double* bulk,
+                                        const double* K_elast_vals, double* K_vals, fem_stream stream) {
+  FEM_REQUIRE(P && DS && shear && bulk && K_elast_vals && K_vals, "null pointer");
+  AsmArgs A;
+  fill_args(P, A);
+  A.DS = DS; A.shear = shear; A.bulk = bulk; A.Kel = K_elast_vals; A.K_vals = K_vals;
+  return launch_assemble<MODE_TANGENT_REF, false>(P, A, (cudaStream_t)stream);
+}
+
+extern "C" int fem_assemble_tangent_force(const fem_plan* P, const double* DS, const double* S, double* K_vals, double* F,
+                                          fem_stream stream) {
+  FEM_REQUIRE(P && DS && S && K_vals && F, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(F) & 15u) == 0, "F must be 16-byte aligned");
+  AsmArgs A;
+  fill_args(P, A);
+  A.DS = DS; A.S = S; A.K_vals = K_vals; A.F = F;
+  return launch_assemble<MODE_TANGENT, true>(P, A, (cudaStream_t)stream);
+}
+
+extern "C" int fem_internal_force(const fem_plan* P, const double* S, double* F, fem_stream stream) {
+  FEM_REQUIRE(P && S && F, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(F) & 15u) == 0, "F must be 16-byte aligned");
+  AsmArgs A;
+  fill_args(P, A);
+  A.S = S; A.F = F;
+  return launch_assemble<MODE_FORCE_ONLY, true>(P, A, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 strain: E = B u, one thread per integration point.  csr_matvec adds the stored entries of a row
+// in ascending column order, i.e. ascending node id, x-dof before y-dof (:1043).
+// ------------------------------------------------------------------------------------------------
+template <int NP, int NQ>
+__global__ void __launch_bounds__(256) strain_kernel(int64_t n_e, const int32_t* __restrict__ elem,
+                                                     const double* __restrict__ dphi1, const double* __restrict__ dphi2,
+                                                     const double* __restrict__ u, double* __restrict__ E) {
+  const int64_t n_int = n_e * NQ;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_int; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = g / NQ;
+    int32_t nd[NP];
+    int pp[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      nd[p] = elem[(int64_t)p * n_e + e];
+      pp[p] = p;
+    }
+#pragma unroll
+    for (int i = 1; i < NP; ++i)  // insertion sort by node id (fully unrolled -> registers)
+#pragma unroll
+      for (int j = i; j > 0; --j)
+        if (nd[j - 1] > nd[j]) {
+          const int32_t tn = nd[j]; nd[j] = nd[j - 1]; nd[j - 1] = tn;
+          const int tp = pp[j]; pp[j] = pp[j - 1]; pp[j - 1] = tp;
+        }
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+      const double2 uv = reinterpret_cast<const double2*>(u)[nd[s]];
+      const double a1 = dphi1[(int64_t)pp[s] * n_int + g], a2 = dphi2[(int64_t)pp[s] * n_int + g];
+      e0 = e0 + a1 * uv.x;
+      e1 = e1 + a2 * uv.y;
+      e2 = (e2 + a2 * uv.x) + a1 * uv.y;
+    }
+    __stcs(E + g, e0);
+    __stcs(E + n_int + g, e1);
+    __stcs(E + 2 * n_int + g, e2);
+  }
+}
+
+extern "C" int fem_strain(const fem_plan* P, const double* u, double* E, fem_stream stream) {
+  FEM_REQUIRE(P && u && E, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15u) == 0, "u must be 16-byte aligned");
+  const int threads = 256;
+  int64_t b = (P->n_int + threads - 1) / threads;
+  if (b > (int64_t)P->sm_count * 2048) b = (int64_t)P->sm_count * 2048;
+  const unsigned blocks = (unsigned)b;
+  cudaStream_t st = (cudaStream_t)stream;
+#define STRAIN(NP, NQ) strain_kernel<NP, NQ><<<blocks, threads, 0, st>>>(P->n_e, P->elem, P->dphi1, P->dphi2, u, E)
+  if (P->n_p == 3 && P->n_q == 1) STRAIN(3, 1);
+  else if (P->n_p == 6 && P->n_q == 7) STRAIN(6, 7);
+  else if (P->n_p == 4 && P->n_q == 4) STRAIN(4, 4);
+  else if (P->n_p == 8 && P->n_q == 9) STRAIN(8, 9);
+  else {
+    fem_set_error("unsupported element n_p=%d n_q=%d", P->n_p, P->n_q);
+    return FEM_ERR_UNSUPPORTED;
+  }
+#undef STRAIN
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}

@@ -1,0 +1,104 @@
+// Shared definitions for the sm_100a FEM kernels.  Compiled with -fmad=false: the assembly,
+// strain and force kernels reproduce scipy's accumulation order bit-for-bit, so the compiler
+// must not contract a*b+c.  Kernels that do not need that (SpMV, PCG) call fma() explicitly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fem_b200.h"
+
+#define FEM_MAX_NP 8
+#define FEM_MAX_NQ 9
+#define FEM_WARP 32
+#define FEM_INVALID_KEY 0xFFFFFFFFu
+
+void fem_set_error(const char* fmt, ...);
+
+struct FemTuning {
+  int return_map_variant;  // 0 auto, 1 scalar/256, 2 double2/128, 3 double2/256
+  int assemble_warps;      // warps per block of the assembly kernel (0 = 4)
+  int spmv_group;          // lanes per node in the SpMV (0 = by degree)
+  int spmv_blocks_per_sm;  // 0 = 32
+};
+extern FemTuning g_fem_tuning;
+
+#define FEM_CUDA_CHECK(expr)                                                                     \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      fem_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return FEM_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+#define FEM_REQUIRE(cond, msg)                                    \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      fem_set_error("invalid argument: %s (%s)", msg, #cond);     \
+      return FEM_ERR_INVALID_ARG;                                 \
+    }                                                             \
+  } while (0)
+
+// Reference-element tables, passed by value as a kernel parameter (<= 1.3 KB).
+struct FemRefElem {
+  double dhat1[FEM_MAX_NP * FEM_MAX_NQ];  // (n_p, n_q) row-major
+  double dhat2[FEM_MAX_NP * FEM_MAX_NQ];
+  double wf[FEM_MAX_NQ];
+};
+
+struct fem_plan {
+  int64_t n_n, n_e, n_int, n_dof, nnz, n_blocks;
+  int n_p, n_q, max_degree, max_inc, sm_count;
+  int meta_words;  // uint32 words of (la, pos[]) metadata per incidence
+  FemRefElem ref;
+  // mesh (device copies owned by the plan)
+  int32_t* elem;  // [n_p][n_e]
+  // node-block pattern and its CSR expansion
+  int32_t* nbr_ptr;  // [n_n+1]
+  int32_t* nbr_idx;  // [n_blocks], sorted per node, contains the node itself
+  int32_t* row_ptr;  // [n_dof+1]
+  int32_t* col_idx;  // [nnz]
+  // node -> element incidences in sliced-ELL(32) layout, ascending element order per node
+  int64_t n_slices;
+  int64_t sell_entries;
+  int32_t* inc_cnt;     // [n_n]
+  int64_t* slice_ptr;   // [n_slices+1] entry offsets
+  uint32_t* inc_key;    // [sell_entries]  (element << 3) | local node, FEM_INVALID_KEY = padding
+  uint32_t* inc_meta;   // [meta_words][sell_entries]  byte-packed: word0 = la | pos0<<8 | pos1<<16 | pos2<<24, ...
+  // geometry
+  double* dphi1;   // [n_p][n_int]
+  double* dphi2;   // [n_p][n_int]
+  double* weight;  // [n_int]
+  // scratch
+  double* dscratch;  // small device scratch (8 doubles)
+  int64_t bytes;
+};
+
+static inline int fem_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 doubles */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// streaming (read-once) loads/stores: keep them out of L1 so that L1 serves the gathers
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream2(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream2(double2* p, double2 v) { __stcs(p, v); }

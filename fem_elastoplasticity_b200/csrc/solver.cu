@@ -1,0 +1,316 @@
+// K7-K9: CSR SpMV on the 2x2 node-block pattern, masked Jacobi-PCG with device-resident scalars.
+// Replaces the dense solve of the reference's Newton loop (Plasticity2D_DP/pythonFEM.py:1062-1066;
+// the boolean-mask extraction K[Q,Q] becomes a projected CG on the full vectors) and provides the
+// energy products of its stopping criterion (:1072-1075).
+//
+// SpMV: GROUP lanes cooperate on one node (two rows).  The pattern is stored once per 2x2 block
+// (nbr_idx, 4 B per 4 values) instead of once per value, so a sweep moves 8 B/nnz of values plus
+// 1 B/nnz of indices instead of CSR's 12 B/nnz.  Row values are read as coalesced double2, x is
+// gathered as one double2 per block through L1/L2.
+#include "common.cuh"
+
+template <int GROUP>
+__global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
+                                                          const int32_t* __restrict__ nbr_idx,
+                                                          const double* __restrict__ vals, const double* __restrict__ x,
+                                                          double* __restrict__ y, const uint8_t* __restrict__ mask,
+                                                          double* dot_out, double* zero_a, double* zero_b) {
+  __shared__ double red[32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar housekeeping for the PCG (see fem_pcg_spmv_dot)
+    if (zero_a) *zero_a = 0.0;
+    if (zero_b) *zero_b = 0.0;
+  }
+  const int sub = threadIdx.x % GROUP;
+  const int64_t groups_per_grid = (int64_t)gridDim.x * (blockDim.x / GROUP);
+  const int64_t n_iter = (n_n + groups_per_grid - 1) / groups_per_grid;
+  double dot = 0.0;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t a = it * groups_per_grid + (int64_t)blockIdx.x * (blockDim.x / GROUP) + threadIdx.x / GROUP;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (a < n_n) {
+      const int p0 = nbr_ptr[a];
+      const int deg = nbr_ptr[a + 1] - p0;
+      const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0);
+      const double2* row1 = row0 + deg;
+      for (int j = sub; j < deg; j += GROUP) {
+        const int m = __ldg(nbr_idx + p0 + j);
+        const double2 v0 = __ldcs(row0 + j), v1 = __ldcs(row1 + j);
+        const double2 xv = __ldg(reinterpret_cast<const double2*>(x) + m);
+        acc0 = fma(v0.x, xv.x, acc0);
+        acc0 = fma(v0.y, xv.y, acc0);
+        acc1 = fma(v1.x, xv.x, acc1);
+        acc1 = fma(v1.y, xv.y, acc1);
+      }
+    }
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) {
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
+    if (sub == 0 && a < n_n) {
+      if (mask) {
+        const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
+        if (!mk.x) acc0 = 0.0;
+        if (!mk.y) acc1 = 0.0;
+      }
+      reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
+      if (dot_out) {
+        const double2 xa = __ldg(reinterpret_cast<const double2*>(x) + a);
+        dot = fma(xa.x, acc0, dot);
+        dot = fma(xa.y, acc1, dot);
+      }
+    }
+  }
+  if (dot_out) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+  }
+}
+
+static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x, double* y, const uint8_t* mask,
+                       double* dot, double* zero_a, double* zero_b, cudaStream_t st) {
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
+  const int threads = 256;
+  int group = P->max_degree <= 4 ? 4 : (P->max_degree <= 12 ? 8 : 16);
+  if (g_fem_tuning.spmv_group == 4 || g_fem_tuning.spmv_group == 8 || g_fem_tuning.spmv_group == 16) group = g_fem_tuning.spmv_group;
+  int64_t blocks = (P->n_n * group + threads - 1) / threads;
+  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 32);  // bounded grid: few dot-product atomics
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (group == 4)
+    spmv_blocks_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b);
+  else if (group == 8)
+    spmv_blocks_kernel<8><<<(unsigned)blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b);
+  else
+    spmv_blocks_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_spmv(const fem_plan* P, const double* K_vals, const double* x, double* y, const uint8_t* free_mask,
+                        double* dot, fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && x && y, "null pointer");
+  return launch_spmv(P, K_vals, x, y, free_mask, dot, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// ---- Jacobi ------------------------------------------------------------------------------------
+__global__ void jacobi_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
+                              const double* __restrict__ vals, const uint8_t* __restrict__ mask, double* __restrict__ minv) {
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_n; a += (int64_t)gridDim.x * blockDim.x) {
+    const int p0 = nbr_ptr[a], deg = nbr_ptr[a + 1] - p0;
+    double d0 = 0.0, d1 = 0.0;
+    for (int j = 0; j < deg; ++j)
+      if (nbr_idx[p0 + j] == a) {
+        d0 = vals[4 * (int64_t)p0 + 2 * j];
+        d1 = vals[4 * (int64_t)p0 + 2 * deg + 2 * j + 1];
+        break;
+      }
+    const bool f0 = mask ? mask[2 * a] != 0 : true, f1 = mask ? mask[2 * a + 1] != 0 : true;
+    minv[2 * a] = (f0 && d0 != 0.0) ? 1.0 / d0 : 0.0;
+    minv[2 * a + 1] = (f1 && d1 != 0.0) ? 1.0 / d1 : 0.0;
+  }
+}
+
+extern "C" int fem_jacobi_setup(const fem_plan* P, const double* K_vals, const uint8_t* free_mask, double* minv,
+                                fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && minv, "null pointer");
+  const int threads = 256;
+  jacobi_kernel<<<(unsigned)fem_div_up(P->n_n, threads), threads, 0, (cudaStream_t)stream>>>(P->n_n, P->nbr_ptr, P->nbr_idx,
+                                                                                            K_vals, free_mask, minv);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+// ---- PCG vector kernels ------------------------------------------------------------------------
+// scal[0] = r'z (even iterations), scal[1] = r'r, scal[2] = r'z (odd iterations), scal[3] = p'Kp, scal[4] = |b|^2.
+// Iteration `it` reads rz_old = scal[(it&1)?2:0] and accumulates rz_new into scal[(it&1)?0:2]; the slot pair
+// {rz_new, r'r} is contiguous either way, so a multi-GPU driver all-reduces two adjacent doubles.
+__device__ __forceinline__ int rz_old_slot(int it) { return (it & 1) ? 2 : 0; }
+__device__ __forceinline__ int rz_new_slot(int it) { return (it & 1) ? 0 : 2; }
+
+__global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* __restrict__ rhs, const double* __restrict__ Kx0,
+                                                       const uint8_t* __restrict__ mask, const double* __restrict__ minv,
+                                                       double* __restrict__ r, double* __restrict__ p, double* scal) {
+  __shared__ double red[32];
+  double rz = 0.0, rr = 0.0, bb = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool fr = mask ? mask[i] != 0 : true;
+    const double b = fr ? rhs[i] : 0.0;
+    const double ri = fr ? (Kx0 ? b - Kx0[i] : b) : 0.0;
+    const double z = minv[i] * ri;
+    r[i] = ri;
+    p[i] = z;
+    rz = fma(ri, z, rz);
+    rr = fma(ri, ri, rr);
+    bb = fma(b, b, bb);
+  }
+  rz = block_sum(rz, red);
+  rr = block_sum(rr, red);
+  bb = block_sum(bb, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + 0, rz);
+    atomicAdd(scal + 1, rr);
+    atomicAdd(scal + 4, bb);
+  }
+}
+
+__global__ void __launch_bounds__(256) pcg_update_xr_kernel(int64_t n2, const double2* __restrict__ p, const double2* __restrict__ q,
+                                                            const double2* __restrict__ minv, double2* __restrict__ x,
+                                                            double2* __restrict__ r, double* scal, int it) {
+  __shared__ double red[32];
+  const double rz_old = scal[rz_old_slot(it)], pq = scal[3];
+  const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pi = p[i], qi = __ldcs(q + i), mi = minv[i];
+    double2 xi = x[i], ri = r[i];
+    xi.x = fma(alpha, pi.x, xi.x);
+    xi.y = fma(alpha, pi.y, xi.y);
+    ri.x = fma(-alpha, qi.x, ri.x);
+    ri.y = fma(-alpha, qi.y, ri.y);
+    x[i] = xi;
+    r[i] = ri;
+    rz = fma(ri.x * mi.x, ri.x, rz);
+    rz = fma(ri.y * mi.y, ri.y, rz);
+    rr = fma(ri.x, ri.x, rr);
+    rr = fma(ri.y, ri.y, rr);
+  }
+  rz = block_sum(rz, red);
+  rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + rz_new_slot(it), rz);
+    atomicAdd(scal + 1, rr);
+  }
+}
+
+__global__ void __launch_bounds__(256) pcg_update_p_kernel(int64_t n2, const double2* __restrict__ r, const double2* __restrict__ minv,
+                                                           double2* __restrict__ p, double* scal, int it) {
+  const double rz_old = scal[rz_old_slot(it)], rz_new = scal[rz_new_slot(it)];
+  const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 ri = r[i], mi = minv[i];
+    double2 pi = p[i];
+    pi.x = fma(beta, pi.x, mi.x * ri.x);
+    pi.y = fma(beta, pi.y, mi.y * ri.y);
+    p[i] = pi;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[3] = 0.0;  // p'Kp is re-accumulated by the next SpMV
+}
+
+static unsigned vec_grid(const int64_t n_items, const int sm_count) {
+  int64_t b = (n_items + 255) / 256;
+  const int64_t cap = (int64_t)(sm_count > 0 ? sm_count : 148) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+static int sm_count_now() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+extern "C" int fem_pcg_init(int64_t n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv,
+                            double* r, double* p, double* scal, fem_stream stream) {
+  FEM_REQUIRE(rhs && minv && r && p && scal && n > 0, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FEM_CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
+  pcg_init_kernel<<<vec_grid(n, sm_count_now()), 256, 0, st>>>(n, rhs, Kx0, free_mask, minv, r, p, scal);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_pcg_spmv_dot(const fem_plan* P, const double* K_vals, const double* p, double* q,
+                                const uint8_t* free_mask, double* scal, int iter, fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && p && q && scal, "null pointer");
+  // zero the slots the following update_xr accumulates into: rz_new(iter) and r'r
+  double* rz_new = scal + ((iter & 1) ? 0 : 2);
+  return launch_spmv(P, K_vals, p, q, free_mask, scal + 3, rz_new, scal + 1, (cudaStream_t)stream);
+}
+
+extern "C" int fem_pcg_update_xr(int64_t n, const double* p, const double* q, const double* minv, double* x, double* r,
+                                 double* scal, int iter, fem_stream stream) {
+  FEM_REQUIRE(p && q && minv && x && r && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
+  pcg_update_xr_kernel<<<vec_grid(n / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
+      n / 2, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q), reinterpret_cast<const double2*>(minv),
+      reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), scal, iter);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_pcg_update_p(int64_t n, const double* r, const double* minv, double* p, double* scal, int iter,
+                                fem_stream stream) {
+  FEM_REQUIRE(r && minv && p && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
+  pcg_update_p_kernel<<<vec_grid(n / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
+      n / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p), scal, iter);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_pcg(const fem_plan* P, const double* K_vals, const double* rhs, const uint8_t* free_mask, double rtol,
+                       int maxit, int check_every, double* x, double* work, int* h_iters, double* h_relres,
+                       fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && rhs && x && work, "null pointer");
+  FEM_REQUIRE(maxit >= 0 && rtol >= 0.0, "maxit/rtol");
+  if (check_every < 1) check_every = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = P->n_dof;
+  double *r = work, *p = work + n, *q = work + 2 * n, *minv = work + 3 * n;
+  double* scal = P->dscratch;
+  int rc;
+  if ((rc = fem_jacobi_setup(P, K_vals, free_mask, minv, stream)) != FEM_OK) return rc;
+  if ((rc = launch_spmv(P, K_vals, x, q, free_mask, nullptr, nullptr, nullptr, st)) != FEM_OK) return rc;  // K x0
+  if ((rc = fem_pcg_init(n, rhs, q, free_mask, minv, r, p, scal, stream)) != FEM_OK) return rc;
+  double h[8];
+  FEM_CUDA_CHECK(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, st));
+  FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+  const double bnorm2 = h[4];
+  const double target2 = rtol * rtol * bnorm2;
+  int it = 0;
+  double rr = h[1];
+  int status = FEM_OK;
+  if (bnorm2 == 0.0 || rr <= target2) {
+    if (h_iters) *h_iters = 0;
+    if (h_relres) *h_relres = bnorm2 > 0.0 ? sqrt(rr / bnorm2) : 0.0;
+    return FEM_OK;
+  }
+  while (it < maxit) {
+    int chunk = check_every < (maxit - it) ? check_every : (maxit - it);
+    for (int k = 0; k < chunk; ++k, ++it) {
+      if ((rc = fem_pcg_spmv_dot(P, K_vals, p, q, free_mask, scal, it, stream)) != FEM_OK) return rc;
+      if ((rc = fem_pcg_update_xr(n, p, q, minv, x, r, scal, it, stream)) != FEM_OK) return rc;
+      if ((rc = fem_pcg_update_p(n, r, minv, p, scal, it, stream)) != FEM_OK) return rc;
+    }
+    FEM_CUDA_CHECK(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FEM_CUDA_CHECK(cudaStreamSynchronize(st));
+    rr = h[1];
+    if (!(rr == rr) || isinf(rr)) {
+      fem_set_error("PCG breakdown: residual norm is not finite after %d iterations", it);
+      status = FEM_ERR_PCG_BREAKDOWN;
+      break;
+    }
+    if (rr <= target2) break;
+  }
+  if (status == FEM_OK && rr > target2) {
+    fem_set_error("PCG did not reach rtol=%g in %d iterations (relres=%g)", rtol, it, sqrt(rr / bnorm2));
+    status = FEM_ERR_PCG_MAXIT;
+  }
+  if (h_iters) *h_iters = it;
+  if (h_relres) *h_relres = sqrt(rr / bnorm2);
+  return status;
+}
+
+extern "C" int fem_energy_norms(const fem_plan* P, const double* K_vals, const double* v0, const double* v1,
+                                const double* v2, double* work, double* out, fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && v0 && v1 && v2 && work && out, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  FEM_CUDA_CHECK(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
+  const double* v[3] = {v0, v1, v2};
+  for (int i = 0; i < 3; ++i) {
+    const int rc = launch_spmv(P, K_vals, v[i], work, nullptr, out + i, nullptr, nullptr, st);
+    if (rc != FEM_OK) return rc;
+  }
+  return FEM_OK;
+}

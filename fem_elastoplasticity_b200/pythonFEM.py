@@ -1,0 +1,223 @@
+"""Drop-in host API: the reference's ``pythonFEM.py`` names and signatures for the hot path, backed by
+the CUDA kernels.  NumPy / SciPy objects in, NumPy / SciPy objects out (same shapes, layouts and
+in-place side effects as the reference); every number is produced on the GPU.
+
+Reference functions mirrored
+  get_elastic_stiffness_matrix   Plasticity2D_DP/pythonFEM.py:491-601 (== tsx-tunnel:432-542); Elasticity2D:368-477
+  construct_constitutive_problem Plasticity2D_DP/pythonFEM.py:604-757; tsx-tunnel/pythonFEM.py:990-1157
+  get_quadrature_volume / get_local_basis_volume / LagrangeElementType   :55-60, :364-488 (host tables)
+Entry points for the statements the reference writes inline in its Newton loop (:1043-1075)
+  strain, assemble_tangent, internal_force, solve_increment (PCG instead of the dense solve), stopping_criterion
+"""
+import enum
+
+import numpy as np
+import scipy.sparse as ssp
+import torch
+
+from .plan import FemPlan, dp_return_map
+
+
+class LagrangeElementType(enum.Enum):
+    P1 = 1
+    P2 = 2
+    Q1 = 3
+    Q2 = 4
+
+
+def flatten_row(v):
+    return np.reshape(v, (1, -1), order='F')
+
+
+def flatten_col(v):
+    return np.reshape(v, (np.size(v), 1), order='F')
+
+
+def get_quadrature_volume(el_type):
+    """(Xi (2,n_q), WF (1,n_q)) - same rules as the reference (:398-410)."""
+    g = 1 / np.sqrt(3)
+    third = 1 / 3
+    if el_type == LagrangeElementType.P1:
+        return np.array([[third], [third]]), np.array([[0.5]])
+    if el_type == LagrangeElementType.P2:
+        p, q, r, s = 0.1012865073235, 0.7974269853531, 0.4701420641051, 0.0597158717898
+        return (np.array([[p, q, p, r, r, s, third], [p, p, q, s, r, r, third]]),
+                0.5 * np.array([[0.1259391805448] * 3 + [0.1323941527885] * 3 + [0.225]]))
+    if el_type == LagrangeElementType.Q1:
+        return np.array([[-g, -g, g, g], [-g, g, -g, g]]), np.array([[1, 1, 1, 1]])
+    if el_type == LagrangeElementType.Q2:
+        return (np.array([[-g, g, g, -g, 0, g, 0, -g, 0], [-g, -g, g, g, -g, 0, g, 0, 0]]),
+                np.array([[25 / 81] * 4 + [40 / 81] * 4 + [64 / 81]]))
+    raise ValueError(f"unsupported element type {el_type}")
+
+
+def get_local_basis_volume(el_type, xi):
+    """(HatP, DHatP1, DHatP2), each (n_p, n_q) (:434-488)."""
+    x, y = xi[0], xi[1]
+    zero = np.zeros(np.size(x, 0))
+    if el_type == LagrangeElementType.P1:
+        return np.array([1 - x - y, x, y]), np.array([[-1], [1], [0]]), np.array([[-1], [0], [1]])
+    if el_type == LagrangeElementType.P2:
+        o = 1 - x - y
+        return (np.array([o * (2 * o - 1), x * (2 * x - 1), y * (2 * y - 1), 4 * x * y, 4 * o * y, 4 * o * x]),
+                np.array([-4 * o + 1, 4 * x - 1, zero, 4 * y, -4 * y, 4 * (o - x)]),
+                np.array([-4 * o + 1, zero, 4 * y - 1, 4 * x, 4 * (o - y), -4 * x]))
+    if el_type == LagrangeElementType.Q1:
+        return (np.array([(1 - x) * (1 - y) / 4, (1 + x) * (1 - y) / 4, (1 + x) * (1 + y) / 4, (1 - x) * (1 + y) / 4]),
+                np.array([-(1 - y) / 4, (1 - y) / 4, (1 + y) / 4, -(1 + y) / 4]),
+                np.array([-(1 - x) / 4, -(1 + x) / 4, (1 + x) / 4, (1 - x) / 4]))
+    if el_type == LagrangeElementType.Q2:
+        xx, yy = pow(x, 2), pow(y, 2)
+        return (np.array([(1 - x) * (1 - y) * (-1 - x - y) / 4, (1 + x) * (1 - y) * (-1 + x - y) / 4,
+                          (1 + x) * (1 + y) * (-1 + x + y) / 4, (1 - x) * (1 + y) * (-1 - x + y) / 4,
+                          (1 - xx) * (1 - y) / 2, (1 + x) * (1 - yy) / 2, (1 - xx) * (1 + y) / 2, (1 - x) * (1 - yy) / 2]),
+                np.array([(1 - y) * (2 * x + y) / 4, (1 - y) * (2 * x - y) / 4, (1 + y) * (2 * x + y) / 4,
+                          (1 + y) * (2 * x - y) / 4, -x * (1 - y), (1 - yy) / 2, -x * (1 + y), -(1 - yy) / 2]),
+                np.array([(1 - x) * (x + 2 * y) / 4, (1 + x) * (-x + 2 * y) / 4, (1 + x) * (x + 2 * y) / 4,
+                          (1 - x) * (-x + 2 * y) / 4, -(1 - xx) / 2, -(1 + x) * y, (1 - xx) / 2, -(1 - x) * y]))
+    raise ValueError(f"unsupported element type {el_type}")
+
+
+# ------------------------------------------------------------------------------------------------
+def _plan_of(obj):
+    if isinstance(obj, FemPlan):
+        return obj
+    plan = getattr(obj, "_fem_plan", None)
+    if plan is None:
+        raise TypeError("expected a FemPlan or a matrix returned by get_elastic_stiffness_matrix")
+    return plan
+
+
+def _host_B(plan, elements):
+    """scipy CSR B (3 n_int x 2 n_n) with the reference's explicit zeros (:549-571); values from the GPU geometry."""
+    n_p, n_q, n_int = plan.n_p, plan.n_q, plan.n_int
+    d1 = plan.dphi1.cpu().numpy()
+    d2 = plan.dphi2.cpu().numpy()
+    node = np.repeat(np.asarray(elements, dtype=np.int64), n_q, axis=1)
+    g = np.arange(n_int)
+    z = np.zeros_like(d1)
+    vals = np.stack([d1, z, d2, z, d2, d1], axis=1)
+    rows = np.broadcast_to(3 * g + np.array([0, 1, 2, 0, 1, 2])[None, :, None], vals.shape)
+    cols = 2 * node[:, None, :] + np.array([0, 0, 0, 1, 1, 1])[None, :, None]
+    return ssp.csr_matrix((vals.ravel(), (rows.ravel(), cols.ravel())), shape=(3 * n_int, plan.n_dof))
+
+
+def _d_indices(n_int):
+    aux = np.arange(3 * n_int).reshape((3, n_int), order='F') + 1
+    return np.tile(aux, (3, 1)), np.repeat(aux, 3, axis=0)
+
+
+def _host_K(plan, k_vals, prune=True):
+    K = plan.to_scipy_csr(k_vals)
+    if prune:
+        K.eliminate_zeros()          # scipy's csr_matmat / binop drop exact zeros
+    K = K.tocsc()
+    K._fem_plan = plan
+    K._fem_vals = k_vals
+    return K
+
+
+def get_elastic_stiffness_matrix(elements, coordinates, shear, bulk, dhatp1, dhatp2, wf, variant="plasticity",
+                                 host_matrices=True, device=None):
+    """K_elast = B^T D B.  ``variant='plasticity'`` (Plasticity2D_DP / tsx-tunnel): 0-based ``elements``, returns
+    ``(K, B, weight, id, jd, D)``.  ``variant='elasticity2d'``: 1-based (possibly float) ``elements`` that are shifted
+    IN PLACE like the reference (Elasticity2D/pythonFEM.py:389), returns ``(K, weight)``.
+    ``K`` is a csc_matrix pruned of exact zeros; ``K._fem_plan`` / ``K._fem_vals`` keep the device plan and values."""
+    if variant == "elasticity2d":
+        elements -= 1
+    plan = FemPlan(np.asarray(elements).astype(np.int64), coordinates, dhatp1, dhatp2, wf, device=device)
+    k_vals = plan.assemble_elastic(shear, bulk)
+    weight = plan.weight.cpu().numpy().reshape(1, -1).copy()
+    K = _host_K(plan, k_vals)
+    if variant == "elasticity2d":
+        return K, weight
+    i_d, j_d = _d_indices(plan.n_int)
+    if not host_matrices:
+        return K, plan, weight, i_d, j_d, None
+    B = _host_B(plan, elements)
+    B._fem_plan = plan
+    vd = plan.elastic_dmat(shear, bulk).cpu().numpy()
+    D = ssp.csr_matrix((vd.ravel(), (i_d.ravel() - 1, j_d.ravel() - 1)))
+    D._fem_plan = plan
+    D._fem_shear, D._fem_bulk = np.asarray(shear, dtype=np.float64), np.asarray(bulk, dtype=np.float64)
+    return K, B, weight, i_d, j_d, D
+
+
+def construct_constitutive_problem(e, *args, apply_plastic_strain=False):
+    """Both reference signatures:
+        construct_constitutive_problem(e, ep_prev, shear, bulk, eta, c, apply_plastic_strain=False)       (Plasticity2D_DP)
+        construct_constitutive_problem(e, e0, ep_prev, shear, bulk, eta, c, apply_plastic_strain=False)   (tsx-tunnel)
+    Returns the reference's dict (s, ds, ind_p, lambda_final, ep) as NumPy arrays.  ``ep_prev`` is updated in place when
+    ``apply_plastic_strain`` (:750-755).  ``lambda_final`` is None whenever an apex point exists, as in the reference
+    (SURVEY B-3); the intended apex multipliers are returned under the extra key ``lambda_apex_intended``."""
+    args = list(args)
+    if len(args) in (6, 7) and isinstance(args[-1], (bool, np.bool_)):
+        apply_plastic_strain = bool(args.pop())
+    if len(args) == 5:
+        e0 = None
+        ep_prev, shear, bulk, eta, c = args
+    elif len(args) == 6:
+        e0, ep_prev, shear, bulk, eta, c = args
+    else:
+        raise TypeError("construct_constitutive_problem: wrong number of arguments")
+    ep_dev = None
+    if ep_prev is not None:
+        ep_dev = torch.as_tensor(np.ascontiguousarray(ep_prev, dtype=np.float64)).cuda()
+    r = dp_return_map(e, ep_dev, shear, bulk, eta, c, apply_plastic_strain=apply_plastic_strain, e0=e0, want_lambda=True)
+    counts = r["counts"].cpu().numpy()
+    ind_p = r["ind_p"].cpu().numpy().astype(bool)
+    lam = r["lambda"].cpu().numpy().reshape(1, -1)
+    ep = r["ep"].cpu().numpy()
+    if apply_plastic_strain and ep_prev is not None:
+        ep_prev[...] = ep                   # the reference returns ep_prev itself, mutated
+        ep = ep_prev
+    out = {'s': r["s"].cpu().numpy(), 'ds': r["ds"].cpu().numpy(), 'ind_p': ind_p,
+           'lambda_final': None if counts[1] > 0 else lam, 'ep': ep,
+           'lambda_apex_intended': lam, 'n_smooth': int(counts[0]), 'n_apex': int(counts[1])}
+    return out
+
+
+# ---- the reference's inline Newton statements as functions ------------------------------------------------
+def strain(plan_or_B, U):
+    """E = reshape(B @ U(:), (3, n_int), 'F') (:1043); U is (2, n_n)."""
+    plan = _plan_of(plan_or_B)
+    u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(-1, order='F'))
+    return plan.strain(u).cpu().numpy()
+
+
+def assemble_tangent(plan_or_K, ds, mode="reference", D_elast=None, K_elast=None):
+    """K_tangent (:1047-1050).  ``mode='reference'`` evaluates K_elast + B^T (D_p - D_elast) B in the reference's own
+    order (bit-identical; needs ``K_elast`` from get_elastic_stiffness_matrix and its ``D``); ``mode='direct'`` sums
+    B^T (w ds) B in one pass (fastest, equal within rounding)."""
+    plan = _plan_of(plan_or_K)
+    if mode == "direct":
+        return _host_K(plan, plan.assemble_tangent(ds))
+    K_elast = plan_or_K if K_elast is None else K_elast
+    if D_elast is None or not hasattr(D_elast, "_fem_shear") or not hasattr(K_elast, "_fem_vals"):
+        raise TypeError("mode='reference' needs K_elast and D returned by get_elastic_stiffness_matrix")
+    vals = plan.assemble_tangent_ref(ds, D_elast._fem_shear, D_elast._fem_bulk, K_elast._fem_vals)
+    return _host_K(plan, vals)
+
+
+def internal_force(plan_or_B, s):
+    """F = B^T vec(w * s[0:3]) as an (n_dof, 1) column (:1058)."""
+    plan = _plan_of(plan_or_B)
+    return plan.internal_force(np.asarray(s, dtype=np.float64)[0:3]).cpu().numpy().reshape(-1, 1)
+
+
+def solve_increment(K_tangent, F, Q, rtol=1e-13, maxit=200000):
+    """dU with dU[Q] = K_tangent[Q,Q]^-1 (-F[Q]) (:1062-1066), by Jacobi-PCG on the device; returns (2, n_n)."""
+    plan = _plan_of(K_tangent)
+    mask = plan.mask_u8(Q)
+    rhs = -np.asarray(F, dtype=np.float64).reshape(-1)
+    x, its, rel = plan.pcg(K_tangent._fem_vals, rhs, mask, rtol=rtol, maxit=maxit)
+    dU = x.cpu().numpy().reshape((2, -1), order='F')
+    return dU
+
+
+def stopping_criterion(K_elast, dU, U_it, U_new):
+    """sqrt(dU'K dU) / (sqrt(U_it'K U_it) + sqrt(U_new'K U_new)) (:1072-1075); inputs (2, n_n)."""
+    plan = _plan_of(K_elast)
+    v = [plan._f64(np.asarray(a, dtype=np.float64).reshape(-1, order='F')) for a in (dU, U_it, U_new)]
+    q = torch.sqrt(plan.energy_norms(K_elast._fem_vals, *v)).cpu().numpy()
+    return q[0] / (q[1] + q[2])

@@ -1,0 +1,150 @@
+/*
+ * fem_b200.h - C ABI of the B200-native FEM elasto-plasticity hot path.
+ *
+ * The reference (MartinBeseda/FEM-ElastoPlasticity) is pure Python and has no FFI;
+ * these entry points are what a ctypes binding of its pythonFEM.py hot path binds
+ * (INTEGRATION.md shows the stub).  Each symbol cites the reference statement it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with h_ (host);
+ *   - all arrays are FP64 / int32 / uint8, structure-of-arrays, C-contiguous:
+ *       elem[n_p][n_e] (0-based), coord[2][n_n], E[3][n_int], S[4][n_int], DS[9][n_int],
+ *       Ep[4][n_int]; nodal vectors are DOF-interleaved: u[2*node + comp]
+ *       (== U.reshape(-1, order='F') of the reference's (2, n_n) arrays);
+ *   - integration point g = e*n_q + q; DS[k] is entry (k%3, k/3) of the 3x3 tangent;
+ *   - K is CSR (int32 row_ptr/col_idx, sorted columns) over the STRUCTURAL pattern of
+ *     B^T D B (2x2 node blocks); values arrays are aligned with fem_plan_pattern();
+ *   - functions return fem_status; fem_last_error_string() describes the last failure
+ *     on the calling thread.  Nothing throws across the ABI.  There is no CPU fallback.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  Kernels are
+ *     asynchronous on it; only functions that return host scalars synchronise.
+ */
+#ifndef FEM_B200_H
+#define FEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fem_plan fem_plan; /* opaque: CSR pattern, incidence lists, geometry, workspaces */
+typedef void* fem_stream;         /* cudaStream_t */
+
+typedef enum fem_status {
+  FEM_OK = 0,
+  FEM_ERR_INVALID_ARG = 1,
+  FEM_ERR_CUDA = 2,
+  FEM_ERR_NONFINITE_JACOBIAN = 3, /* degenerate element: det == 0 or non-finite (reference lets inf/nan propagate) */
+  FEM_ERR_PCG_BREAKDOWN = 4,      /* p'Ap <= 0 or non-finite */
+  FEM_ERR_PCG_MAXIT = 5,          /* not converged in maxit iterations (x holds the last iterate) */
+  FEM_ERR_UNSUPPORTED = 6,        /* element type / node valence outside the compiled kernels */
+  FEM_ERR_NO_DEVICE = 7
+} fem_status;
+
+const char* fem_last_error_string(void);
+int fem_version(void);
+/* sm_count, compute capability and free/total HBM bytes of the current device */
+int fem_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* free_bytes, int64_t* total_bytes);
+
+/* ---- plan: mesh topology -> structural CSR pattern + geometry (once per mesh) -----------------
+ * Replaces the geometry/B/D part of get_elastic_stiffness_matrix
+ * (Plasticity2D_DP/pythonFEM.py:500-592 == tsx-tunnel/pythonFEM.py:441-533 == Elasticity2D/pythonFEM.py:375-467)
+ * and the implicit pattern construction of scipy's coo_tocsr/csr_matmat (:570,592,595).
+ * h_dhatp1/h_dhatp2 are (n_p, n_q) row-major, h_wf is (n_q,): the outputs of
+ * get_local_basis_volume / get_quadrature_volume, accepted unchanged.
+ * Supported (n_p, n_q): (3,1) P1, (6,7) P2, (4,4) Q1, (8,9) Q2.                                  */
+int fem_plan_create(int64_t n_n, int64_t n_e, int n_p, int n_q, const int32_t* elem, const double* coord,
+                    const double* h_dhatp1, const double* h_dhatp2, const double* h_wf, fem_stream stream,
+                    fem_plan** out);
+int fem_plan_destroy(fem_plan* plan);
+/* n_n, n_e, n_int, n_dof, nnz, max node degree (neighbours incl. self) */
+int fem_plan_sizes(const fem_plan* plan, int64_t* n_n, int64_t* n_e, int64_t* n_int, int64_t* n_dof, int64_t* nnz,
+                   int* max_degree);
+/* structural CSR pattern (device pointers owned by the plan; row_ptr has n_dof+1 entries) */
+int fem_plan_pattern(const fem_plan* plan, const int32_t** row_ptr, const int32_t** col_idx, int64_t* nnz);
+/* node-block form of the same pattern used by the SpMV: nbr_ptr[n_n+1], nbr_idx[nnz/4] */
+int fem_plan_blocks(const fem_plan* plan, const int32_t** nbr_ptr, const int32_t** nbr_idx, int64_t* n_blocks);
+/* dphi1, dphi2 (n_p, n_int) and weight (n_int,) = |det J| * wf  (:545-546, :585); owned by the plan.
+ * These are exactly the stored values of the reference's sparse B (:549-571).                    */
+int fem_plan_geometry(const fem_plan* plan, const double** dphi1, const double** dphi2, const double** weight);
+/* bytes of device memory held by the plan */
+int64_t fem_plan_bytes(const fem_plan* plan);
+
+/* vd[k][g] = (2*Dev[k]*G + Vol[k]*K) * weight[g], k < 9: the stored values of the reference's sparse D
+ * (Plasticity2D_DP/pythonFEM.py:579-592), for callers that need D_elast itself.                   */
+int fem_elastic_dmat(const fem_plan* plan, const double* shear, const double* bulk, double* vd, fem_stream stream);
+
+/* ---- assembly ---------------------------------------------------------------------------------
+ * K_elast = B^T D B, D = weight*(2G*Dev + K*Vol)          (Plasticity2D_DP/pythonFEM.py:579-595)
+ * Values are accumulated per CSR entry in ascending (element, quadrature point, strain row) order,
+ * i.e. the order of scipy's csr_matmat, without FMA contraction: bit-identical to the reference. */
+int fem_assemble_elastic(const fem_plan* plan, const double* shear, const double* bulk, double* K_vals,
+                         fem_stream stream);
+/* K_tangent, direct form: sum_g B_g^T (w_g * DS_g) B_g     (Plasticity2D_DP/pythonFEM.py:1047-1050,
+ * tsx-tunnel/pythonFEM.py:1773-1777; equal to the reference within rounding, one pass, K written once) */
+int fem_assemble_tangent(const fem_plan* plan, const double* DS, double* K_vals, fem_stream stream);
+/* K_tangent in the reference's own operation order: K_elast + B^T (D_p - D_elast) B  (:1050);
+ * bit-identical to the reference; reads K_elast_vals and shear/bulk in addition.                 */
+int fem_assemble_tangent_ref(const fem_plan* plan, const double* DS, const double* shear, const double* bulk,
+                             const double* K_elast_vals, double* K_vals, fem_stream stream);
+/* Fused Newton-iteration assembly: K_tangent (direct form) and F = B^T (w*S[0:3]) in one pass.   */
+int fem_assemble_tangent_force(const fem_plan* plan, const double* DS, const double* S, double* K_vals, double* F,
+                               fem_stream stream);
+
+/* E = reshape(B @ U(:), (3, n_int), 'F')                    (Plasticity2D_DP/pythonFEM.py:1043,1095) */
+int fem_strain(const fem_plan* plan, const double* u, double* E, fem_stream stream);
+/* F = B^T vec(w * S[0:3])  (S has leading dimension n_int)  (Plasticity2D_DP/pythonFEM.py:1058) */
+int fem_internal_force(const fem_plan* plan, const double* S, double* F, fem_stream stream);
+
+/* ---- Drucker-Prager return map + consistent tangent -------------------------------------------
+ * construct_constitutive_problem (Plasticity2D_DP/pythonFEM.py:604-757; tsx-tunnel/pythonFEM.py:990-1157).
+ * h_e0: host 4-vector added to the strain (tsx signature) or NULL.  Ep_prev may be NULL (treated as 0).
+ * apply != 0: Ep_prev is updated IN PLACE (the reference aliases ep = ep_prev, :750-755) and, if Ep_out is
+ * non-NULL and != Ep_prev, also copied there; apply == 0: Ep_out (if non-NULL) is zero-filled (:749).
+ * ind_p: uint8 flags CRIT1 > 0.  lambda (nullable): plastic multipliers, smooth branch as the reference
+ * (:710); apex entries hold the intended (eta*p_tr - c)/denom_a (the reference's outer-product expression
+ * at :714 makes its lambda_final None; not under parity).  counts (nullable): device int64[2] =
+ * {n_smooth, n_apex}, ADDED to (zero it first) - the numbers the reference logs at :730.          */
+int fem_dp_return_map(int64_t n_int, const double* E, const double* h_e0, double* Ep_prev, const double* shear,
+                      const double* bulk, const double* eta, const double* c, int apply, double* S, double* DS,
+                      uint8_t* ind_p, double* lambda, double* Ep_out, int64_t* counts, fem_stream stream);
+
+/* ---- CSR SpMV + PCG (replaces the dense solve, Plasticity2D_DP/pythonFEM.py:1062-1066, and serves
+ * the energy-norm criterion, :1072-1075) ----------------------------------------------------------
+ * y = mask .* (K x); free_mask (uint8[n_dof], nullable = all free).  If dot != NULL, x'y over the
+ * masked rows is ADDED to *dot (device double).                                                   */
+int fem_spmv(const fem_plan* plan, const double* K_vals, const double* x, double* y, const uint8_t* free_mask,
+             double* dot, fem_stream stream);
+/* minv[i] = free_mask[i] ? 1/K[i,i] : 0   (Jacobi preconditioner with the Dirichlet rows removed) */
+int fem_jacobi_setup(const fem_plan* plan, const double* K_vals, const uint8_t* free_mask, double* minv,
+                     fem_stream stream);
+/* PCG building blocks (device-resident scalars; used directly by the multi-GPU driver, which inserts
+ * the halo exchange and the NCCL all-reduces between them).  scal is a device double[8]:
+ * scal[0]=rz (even iterations), scal[1]=r'r, scal[2]=rz (odd iterations), scal[3]=p'Kp, scal[4]=|b|^2. */
+int fem_pcg_init(int64_t n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv,
+                 double* r, double* p, double* scal, fem_stream stream);
+int fem_pcg_spmv_dot(const fem_plan* plan, const double* K_vals, const double* p, double* q,
+                     const uint8_t* free_mask, double* scal, int iter, fem_stream stream);
+int fem_pcg_update_xr(int64_t n, const double* p, const double* q, const double* minv, double* x, double* r,
+                      double* scal, int iter, fem_stream stream);
+int fem_pcg_update_p(int64_t n, const double* r, const double* minv, double* p, double* scal, int iter,
+                     fem_stream stream);
+/* Single-GPU Jacobi-PCG on K[Q,Q] x[Q] = rhs[Q], x[~Q] left untouched at 0.  work: 4*n_dof doubles.
+ * Stops when |r| <= rtol*|rhs| (checked every check_every iterations).  Synchronises.            */
+int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const uint8_t* free_mask, double rtol,
+            int maxit, int check_every, double* x, double* work, int* h_iters, double* h_relres, fem_stream stream);
+
+/* energy products for the Newton stopping criterion: out[i] = v_i' K v_i, i < 3 (device double[3], overwritten) */
+int fem_energy_norms(const fem_plan* plan, const double* K_vals, const double* v0, const double* v1, const double* v2,
+                     double* work, double* out, fem_stream stream);
+
+/* launch-shape knobs for benchmarking ("return_map_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm");
+ * value 0 restores the default.  Results never depend on them.                                     */
+int fem_set_tuning(const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEM_B200_H */
