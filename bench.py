@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py - the north-star hot path on synthetic refined P1 meshes (BASELINE.json config 4/5).
+
+A *step* is one Newton-iteration pass of the hot path over one mesh, all inputs resident in HBM:
+    strain E = B u  ->  Drucker-Prager return map  ->  K_tangent assembly + internal force (one pass)
+      ->  Jacobi-PCG on K_tangent[Q,Q] (a FIXED number of iterations, --pcg-iters)  ->  energy-norm criterion
+`value` is the first component of BASELINE.json's metric, K_tangent assembly throughput in Melem/s
+(elements of all ranks / CUDA-event time of the assembly kernel inside the timed steps, max over ranks);
+`parts` carries the other two components (DP return map Mpts/s, PCG-Newton s/step with ms/iteration) and
+`rooflines` the achieved HBM bandwidth of every kernel against MEASURED_PEAKS.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--nx 2828] [--pcg-iters 20]
+    python bench.py --impl reference      # the oracle port of the reference's CPU path on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "K_tangent assembly Melem/s + DP return-map Mpts/s + PCG-Newton s/step; %HBM roof"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference path (NumPy/SciPy, single-threaded like the reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(nx, pcg_iters, steps, warmup, seed=0):
+    """Times the reference's statements (restated in oracle/fem_oracle.py) on an nx x nx P1 mesh."""
+    import scipy.sparse.linalg as spla
+    from oracle import fem_oracle as fo
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    m = fo.square_mesh_p1(nx, nx, 10.0, 10.0)
+    n_e = m["elements"].shape[1]
+    G0, K0, eta0, c0, _ = fo.footing_constants()
+    G, Kb, eta, c = (v * np.ones(n_e) for v in (G0, K0, eta0, c0))
+    t0 = time.perf_counter()
+    K, B, w, i_d, j_d, D = fo.elastic_stiffness(m["elements"], m["coordinates"], G, Kb, d1, d2, wf)
+    t_elastic = time.perf_counter() - t0
+    rng = np.random.default_rng(seed)
+    E0 = np.array([[-3e-4], [-3e-4], [0.0]]) + 2e-4 * rng.standard_normal((3, n_e))
+    U = 1e-3 * rng.standard_normal(m["coordinates"].shape)
+    qf = m["Q"].flatten(order="F")
+    t = {"strain": [], "return_map": [], "tangent": [], "force": [], "pcg": [], "criterion": [], "step": []}
+    for s in range(warmup + steps):
+        a = time.perf_counter()
+        fo.strain(B, U)
+        b = time.perf_counter()
+        cp = fo.constitutive_problem(E0.copy(), np.zeros((4, n_e)), G, Kb, eta, c)
+        c_ = time.perf_counter()
+        Kt = fo.tangent_stiffness(K, B, D, w, cp["ds"], i_d, j_d)
+        d = time.perf_counter()
+        F = fo.internal_force(B, w, cp["s"])
+        e = time.perf_counter()
+        Kqq = Kt.tocsr()[qf][:, qf]
+        dinv = 1.0 / Kqq.diagonal()
+        e2 = time.perf_counter()                                  # the extraction is not counted as PCG time
+        spla.cg(Kqq, -F[qf], rtol=0.0, atol=0.0, maxiter=pcg_iters, M=spla.LinearOperator(Kqq.shape, lambda v: dinv * v))
+        f = time.perf_counter()
+        u = U.flatten(order="F")
+        fo.newton_criterion(K, u, u, u)
+        g = time.perf_counter()
+        if s >= warmup:
+            for k, v in zip(("strain", "return_map", "tangent", "force", "pcg", "criterion"), (b - a, c_ - b, d - c_, e - d, f - e2, g - f)):
+                t[k].append(v)
+            t["step"].append((g - a) - (e2 - e))
+    mean = {k: float(np.mean(v)) for k, v in t.items()}
+    return {"n_e": n_e, "n_dof": int(2 * m["coordinates"].shape[1]), "nnz": int(K.nnz), "t": mean, "t_elastic": t_elastic}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx = args.cpu_nx
+    r = cpu_reference_pass(nx, args.pcg_iters, args.steps, args.warmup)
+    melem = r["n_e"] / r["t"]["tangent"] / 1e6
+    sample = (f"oracle port (NumPy/SciPy restatement of Plasticity2D_DP/pythonFEM.py:1043-1075) on a {nx}x{nx} P1 mesh = "
+              f"{r['n_e']} elements, {args.pcg_iters} SciPy-CG iterations/step; /root/reference is pure Python and does not travel")
+    line = {"impl": "reference", "metric": METRIC, "value": melem, "unit": "Melem/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["t"]["step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"P1 uniform mesh {nx}x{nx} cells ({r['n_e']} elements): bounded sample of config 4", "pcg_iters": args.pcg_iters},
+            "parts": {"return_map_mpts_s": r["n_e"] / r["t"]["return_map"] / 1e6, "pcg_ms_per_iter": 1e3 * r["t"]["pcg"] / max(args.pcg_iters, 1),
+                      "newton_step_s": r["t"]["step"], "strain_ms": 1e3 * r["t"]["strain"], "force_ms": 1e3 * r["t"]["force"],
+                      "elastic_assembly_melem_s": r["n_e"] / r["t_elastic"] / 1e6},
+            "cpu_baseline": {"value": melem, "unit": "Melem/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": melem, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from fem_elastoplasticity_b200 import meshgen, distributed as fdist
+    from fem_elastoplasticity_b200 import pythonFEM as api
+    from fem_elastoplasticity_b200.plan import FemPlan, dp_return_map
+
+    nx = args.nx
+    et = api.LagrangeElementType.P1
+    xi, wf = api.get_quadrature_volume(et)
+    _, d1, d2 = api.get_local_basis_volume(et, xi)
+    # weak scaling: rank r owns cell rows [r*nx, (r+1)*nx) of an nx x (nx*world) mesh plus one ghost cell row per neighbour
+    part = fdist.StripPartition(nx, nx * world, rank, world, size_x=10.0, size_y=10.0 * world)
+    mesh = part.local_mesh(dev)
+    t_plan0 = time.perf_counter()
+    P = FemPlan(mesh["elements"], mesh["coordinates"], d1, d2, wf, device=dev)
+    torch.cuda.synchronize()
+    t_plan = time.perf_counter() - t_plan0
+    n_e_owned = part.n_e_owned
+    G, Kb, eta, c = meshgen.footing_materials(P.n_int, dev)
+    Es = meshgen.synthetic_strain(P.n_int, dev, seed=rank)
+    u = 1e-3 * torch.randn(P.n_dof, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+    mask = part.free_owned_mask(P, mesh)
+    E = P.empty(3, P.n_int)
+    rm = {}
+    k_tan, F = P.empty(P.nnz), P.empty(P.n_dof)
+    k_el = P.assemble_elastic(G, Kb)
+    pcg = fdist.DistributedPCG(P, part, mask)
+    rhs = P.empty(P.n_dof)
+    from fem_elastoplasticity_b200.plan import axpby
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    phases = ("strain", "return_map", "assembly", "pcg", "criterion")
+    launches = {"n": 0}
+
+    def step(record=None):
+        evs = [ev() for _ in range(len(phases) + 1)]
+        evs[0].record()
+        P.strain(u, out=E)
+        evs[1].record()
+        dp_return_map(Es, None, G, Kb, eta, c, want_ep=False, out=rm)
+        evs[2].record()
+        P.assemble_tangent_force(rm["ds"], rm["s"], out_k=k_tan, out_f=F)
+        evs[3].record()
+        axpby(-1.0, F, 0.0, F, out=rhs)
+        x, its = pcg.solve(k_tan, rhs, iters=args.pcg_iters)
+        evs[4].record()
+        pcg.energy_norms(k_el, x, u, rhs)
+        evs[5].record()
+        launches["n"] = 1 + 1 + 1 + 1 + pcg.launches_last + 3
+        if record is not None:
+            record.append(evs)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rec = []
+    torch.cuda.synchronize()
+    t0 = ev()
+    t1 = ev()
+    t0.record()
+    for _ in range(args.steps):
+        step(rec)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t0.elapsed_time(t1)
+    per = {p: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in rec])) for i, p in enumerate(phases)}
+    # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    ds_host = torch.empty((9, P.n_int), dtype=torch.float64, pin_memory=True)
+    ds_host.copy_(rm["ds"])
+    k_host = torch.empty(P.nnz, dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 3))
+    for i in range(1 + e2e_steps):
+        if i == 1:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a0 = ev()
+            a1 = ev()
+            a0.record()
+        ds_dev = ds_host.to(dev, non_blocking=True)
+        kv = P.assemble_tangent(ds_dev)
+        k_host.copy_(kv, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    a1.record()
+    torch.cuda.synchronize()
+    e2e_ms = a0.elapsed_time(a1) / e2e_steps
+    # ---- reduce over ranks (max time)
+    vec = torch.tensor([total_ms, per["strain"], per["return_map"], per["assembly"], per["pcg"], per["criterion"], e2e_ms],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+    total_ms, t_strain, t_rm, t_asm, t_pcg, t_crit, e2e_ms = [float(v) for v in vec.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_e_tot = n_e_owned * world
+    n_int_tot = n_e_tot
+    n_dof_rank, nnz_rank = P.n_dof, P.nnz
+    peak, peak_src = measured_peak()
+    ms_step = total_ms / args.steps
+    gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
+    algo = {
+        "assembly": 212.0 * P.n_e + 24.0 * P.n_int + 8.0 * P.n_dof,
+        "return_map": 193.0 * P.n_int,
+        "strain": 12.0 * P.n_e + 8.0 * P.n_dof + 24.0 * P.n_int,
+        "pcg_iter": 12.0 * nnz_rank + 148.0 * n_dof_rank,
+        "spmv": 12.0 * nnz_rank + 4.0 * (n_dof_rank + 1) + 16.0 * n_dof_rank,
+    }
+    pcg_ms_iter = t_pcg / max(args.pcg_iters, 1)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("assemble_rows_kernel")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "assemble_rows_kernel<3,1,TANGENT,FORCE> (K_tangent + F, one pass)",
+            "achieved": gbs(algo["assembly"], t_asm), "peak": peak, "unit": "GB/s", "frac": gbs(algo["assembly"], t_asm) / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["assembly"],
+            "frac_of_8TBs_nominal": gbs(algo["assembly"], t_asm) / 8000.0}
+    rooflines = {k: {"achieved": gbs(algo[a], ms), "frac": gbs(algo[a], ms) / peak, "ms": ms, "algorithmic_bytes": algo[a]}
+                 for k, a, ms in (("dp_return_map", "return_map", t_rm), ("strain", "strain", t_strain),
+                                  ("pcg_iteration(spmv+2 vector kernels)", "pcg_iter", pcg_ms_iter),
+                                  ("criterion(3 spmv)", "spmv", t_crit / 3.0))}
+    line = {
+        "metric": METRIC, "value": n_e_tot / (t_asm * 1e-3) / 1e6, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 4: synthetic uniform P1 mesh {nx}x{nx * world} cells, {n_e_tot} elements "
+                               f"({n_e_owned} per GPU, strip partition), DP return map + tangent assembly + PCG",
+                   "n_elements": n_e_tot, "n_dof_per_gpu": n_dof_rank, "nnz_per_gpu": nnz_rank, "pcg_iters_per_step": args.pcg_iters,
+                   "preconditioner": "jacobi", "plastic_fraction": float(rm["ind_p"].double().mean().item()),
+                   "l2": "inputs larger than L2 (>=1 GB per array vs 126 MB), no flush needed",
+                   "plan_build_s": t_plan, "plan_bytes": P.bytes},
+        "parts": {"tangent_assembly_melem_s": n_e_tot / (t_asm * 1e-3) / 1e6, "return_map_mpts_s": n_int_tot / (t_rm * 1e-3) / 1e6,
+                  "pcg_newton_s_per_step": ms_step * 1e-3, "pcg_ms_per_iter": pcg_ms_iter, "strain_ms": t_strain, "criterion_ms": t_crit,
+                  "assembly_ms": t_asm, "return_map_ms": t_rm, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
+        "roofline": roof, "rooflines": rooflines, "clocks": clocks,
+        "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
+                "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent on pinned host DS -> host K values"},
+        "gpu_launches": int(launches["n"] * args.steps),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_pass(args.cpu_nx, args.pcg_iters, 1, 0)
+        line["cpu_baseline"] = {"value": r["n_e"] / r["t"]["tangent"] / 1e6, "unit": "Melem/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle port of Plasticity2D_DP/pythonFEM.py:1047-1050 on {args.cpu_nx}x{args.cpu_nx} cells "
+                                          f"({r['n_e']} elements, 1/{max(1, n_e_tot // r['n_e'])} of the workload); host has {os.cpu_count()} cores, "
+                                          "the reference path is single-threaded",
+                                "return_map_mpts_s": r["n_e"] / r["t"]["return_map"] / 1e6,
+                                "pcg_ms_per_iter": 1e3 * r["t"]["pcg"] / max(args.pcg_iters, 1), "newton_step_s": r["t"]["step"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--nx", type=int, default=2828, help="cells per side per GPU (2828 -> 15 995 168 elements, config 4)")
+    ap.add_argument("--pcg-iters", type=int, default=20)
+    ap.add_argument("--cpu-nx", type=int, default=500, help="mesh side of the bounded CPU sample")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -51,6 +51,8 @@ SIGNATURES = {
     "fem_pcg_update_p": [_i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "fem_pcg": [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl), _vp],
     "fem_energy_norms": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fem_vec_axpby": [_i64, _dbl, _vp, _dbl, _vp, _vp, _vp],
+    "fem_transform": [_vp, _vp, _vp, _vp],
     "fem_set_tuning": [C.c_char_p, _i32],
 }
 _RESTYPE = {"fem_last_error_string": C.c_char_p, "fem_plan_bytes": _i64}

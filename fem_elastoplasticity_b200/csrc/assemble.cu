@@ -322,3 +322,36 @@ extern "C" int fem_strain(const fem_plan* P, const double* u, double* E, fem_str
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
+
+// transform(): one thread per node walks its incidence list (Plasticity2D_DP/pythonFEM.py:760-816)
+__global__ void transform_kernel(int64_t n_n, int64_t n_slices, int n_q, const int64_t* __restrict__ slice_ptr,
+                                 const uint32_t* __restrict__ inc_key, const double* __restrict__ weight,
+                                 const double* __restrict__ q_int, double* __restrict__ q_node) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slice = a >> 5;
+  if (slice >= n_slices) return;
+  const int lane = (int)(a & 31);
+  const int64_t sbase = slice_ptr[slice];
+  const int width = (int)((slice_ptr[slice + 1] - sbase) >> 5);
+  double num = 0.0, den = 0.0;
+  for (int i = 0; i < width; ++i) {
+    const uint32_t key = inc_key[sbase + (int64_t)i * 32 + lane];
+    if (key == FEM_INVALID_KEY) continue;
+    const int64_t e = key >> 3;
+    for (int q = 0; q < n_q; ++q) {
+      const double w = weight[e * n_q + q];
+      num = num + w * q_int[e * n_q + q];
+      den = den + w;
+    }
+  }
+  if (a < n_n) q_node[a] = num / den;
+}
+
+extern "C" int fem_transform(const fem_plan* P, const double* q_int, double* q_node, fem_stream stream) {
+  FEM_REQUIRE(P && q_int && q_node, "null pointer");
+  const int threads = 128;
+  transform_kernel<<<(unsigned)fem_div_up(P->n_slices * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      P->n_n, P->n_slices, P->n_q, P->slice_ptr, P->inc_key, P->weight, q_int, q_node);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}

@@ -314,3 +314,16 @@ extern "C" int fem_energy_norms(const fem_plan* P, const double* K_vals, const d
   }
   return FEM_OK;
 }
+
+__global__ void axpby_kernel(int64_t n, double a, const double* x, double b, const double* y, double* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + b * y[i];
+}
+
+extern "C" int fem_vec_axpby(int64_t n, double a, const double* x, double b, const double* y, double* out, fem_stream stream) {
+  FEM_REQUIRE(x && y && out && n >= 0, "null pointer");
+  if (n == 0) return FEM_OK;
+  axpby_kernel<<<vec_grid(n, sm_count_now()) * 4, 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y, out);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}

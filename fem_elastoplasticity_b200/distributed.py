@@ -1,0 +1,163 @@
+"""Multi-GPU layer: element-block (strip) partition by coordinate bisection along y, one process per GPU.
+
+Assembly, strain, return map and internal force shard with NO communication: every rank also holds the
+one layer of ghost elements that touches its owned nodes, so its owned matrix rows are complete
+(owner-computes).  Only the PCG communicates: before each SpMV the interface DOFs of the
+search direction are exchanged with the two neighbouring strips (one contiguous node row each way,
+2(nx+1) doubles), and the dot products are all-reduced as device-resident scalars (one scalar after the SpMV,
+one adjacent pair {r'z, r'r} after the vector update).  Collectives go through torch.distributed
+(NCCL on GPUs; gloo in the CPU tests of the host logic).
+
+The reference has no distributed code at all; the single-rank path below is the same
+sequence of kernels with the collectives skipped."""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+class StripPartition:
+    """Rank r owns cell rows [r*ny_loc, (r+1)*ny_loc) of an nx x ny_global uniform P1 mesh and the node rows
+    (r*ny_loc, (r+1)*ny_loc] (rank 0 also owns node row 0): interface nodes belong to the lower rank."""
+
+    def __init__(self, nx, ny_global, rank, world, size_x=10.0, size_y=10.0):
+        if ny_global % world:
+            raise ValueError("ny_global must be divisible by the number of ranks")
+        self.nx, self.ny_global, self.rank, self.world = nx, ny_global, rank, world
+        self.size_x, self.size_y = size_x, size_y
+        self.ny_loc = ny_global // world
+        self.iy0 = rank * self.ny_loc                                   # first local cell/node row (global index)
+        self.has_lower = rank > 0
+        self.has_upper = rank < world - 1
+        self.n_cell_rows = self.ny_loc + (1 if self.has_upper else 0)   # + ghost cell row above
+        self.n_node_rows = self.n_cell_rows + 1
+        self.row_dofs = 2 * (nx + 1)
+        self.first_owned_row = 1 if self.has_lower else 0               # local node-row indices
+        self.last_owned_row = self.ny_loc
+        self.n_e_owned = 2 * nx * self.ny_loc
+        self.n_n_local = (nx + 1) * self.n_node_rows
+
+    def local_mesh(self, device):
+        from . import meshgen
+        return meshgen.square_mesh_p1(self.nx, self.n_cell_rows, self.size_x, self.size_y, device=device, iy0=self.iy0,
+                                      n_y_global=self.ny_global, size_y_global=self.size_y)
+
+    def owned_dof_range(self):
+        return self.first_owned_row * self.row_dofs, (self.last_owned_row + 1) * self.row_dofs
+
+    def owned_mask(self, device):
+        m = torch.zeros(self.n_n_local * 2, dtype=torch.uint8, device=device)
+        lo, hi = self.owned_dof_range()
+        m[lo:hi] = 1
+        return m
+
+    def free_owned_mask(self, plan, mesh):
+        """uint8 DOF mask: free (not Dirichlet) AND owned by this rank."""
+        return plan.mask_u8(mesh["Q"]) & self.owned_mask(plan.device)
+
+    def row_slice(self, v, row):
+        return v[row * self.row_dofs:(row + 1) * self.row_dofs]
+
+    def halo_exchange(self, v):
+        """Fill the ghost node rows of the DOF vector ``v`` from the neighbouring strips (no-op on one rank)."""
+        if self.world == 1:
+            return
+        ops = []
+        if self.has_upper:   # my top owned row -> upper rank's bottom ghost row; its first owned row -> my top ghost row
+            ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.last_owned_row), self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, self.row_slice(v, self.last_owned_row + 1), self.rank + 1))
+        if self.has_lower:
+            ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.first_owned_row), self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, self.row_slice(v, 0), self.rank - 1))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def all_reduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t)
+
+
+class CudaOps:
+    """The PCG step kernels of the C ABI (include/fem_b200.h) on one plan."""
+
+    def __init__(self, plan):
+        from .plan import _ptr, _stream
+        from ._lib import call
+        self.plan, self._ptr, self._stream, self._call = plan, _ptr, _stream, call
+        self.n = plan.n_dof
+
+    def new_vec(self, n=None):
+        return torch.zeros(self.n if n is None else n, dtype=torch.float64, device=self.plan.device)
+
+    def jacobi(self, k, mask, out):
+        self.plan.jacobi(k, mask, out=out)
+
+    def pcg_init(self, rhs, kx0, mask, minv, r, p, scal):
+        self._call("fem_pcg_init", self.n, self._ptr(rhs), self._ptr(kx0), self._ptr(mask), self._ptr(minv), self._ptr(r),
+                   self._ptr(p), self._ptr(scal), self._stream())
+
+    def spmv_dot(self, k, p, q, mask, scal, it):
+        self._call("fem_pcg_spmv_dot", self.plan._h, self._ptr(k), self._ptr(p), self._ptr(q), self._ptr(mask), self._ptr(scal),
+                   int(it), self._stream())
+
+    def update_xr(self, p, q, minv, x, r, scal, it):
+        self._call("fem_pcg_update_xr", self.n, self._ptr(p), self._ptr(q), self._ptr(minv), self._ptr(x), self._ptr(r),
+                   self._ptr(scal), int(it), self._stream())
+
+    def update_p(self, r, minv, p, scal, it):
+        self._call("fem_pcg_update_p", self.n, self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), self._stream())
+
+    def spmv(self, k, x, y, mask, dot):
+        self.plan.spmv(k, x, mask=mask, out=y, dot=dot)
+
+
+class DistributedPCG:
+    """Jacobi-PCG over a strip partition.  ``ops`` defaults to the CUDA kernels; the CPU tests inject a
+    NumPy implementation of the same five steps to exercise partition + halo + reduction logic under gloo."""
+
+    def __init__(self, plan, part, mask, ops=None):
+        self.part, self.mask = part, mask
+        self.ops = ops if ops is not None else CudaOps(plan)
+        o = self.ops
+        self.r, self.p, self.q, self.x, self.minv = (o.new_vec() for _ in range(5))
+        self.scal = o.new_vec(8)
+        self.en = o.new_vec(3)
+        self.owned = part.owned_mask(self.r.device)
+        self.launches_last = 0
+
+    def solve(self, k_vals, rhs, iters=None, rtol=1e-10, maxit=100000, check_every=50):
+        """Fixed ``iters`` iterations (benchmarks) or until |r| <= rtol |b|.  Returns (x, iterations)."""
+        o, part, scal = self.ops, self.part, self.scal
+        o.jacobi(k_vals, self.mask, self.minv)
+        self.x.zero_()
+        o.pcg_init(rhs, None, self.mask, self.minv, self.r, self.p, scal)
+        part.all_reduce(scal[0:5])
+        n_it = iters if iters is not None else maxit
+        it = 0
+        self.launches_last = 3
+        while it < n_it:
+            part.halo_exchange(self.p)
+            o.spmv_dot(k_vals, self.p, self.q, self.mask, scal, it)
+            part.all_reduce(scal[3:4])
+            o.update_xr(self.p, self.q, self.minv, self.x, self.r, scal, it)
+            part.all_reduce(scal[1:3] if it % 2 == 0 else scal[0:2])
+            o.update_p(self.r, self.minv, self.p, scal, it)
+            it += 1
+            self.launches_last += 3
+            if iters is None and it % check_every == 0:
+                h = scal.cpu()
+                if not torch.isfinite(h[1]):
+                    raise ArithmeticError("PCG breakdown: residual is not finite")
+                if h[1] <= rtol * rtol * h[4]:
+                    break
+        part.halo_exchange(self.x)
+        return self.x, it
+
+    def energy_norms(self, k_vals, v0, v1, v2):
+        """v_i' K v_i over the whole (distributed) DOF set; returns a device tensor of 3 doubles."""
+        self.en.zero_()
+        for i, v in enumerate((v0, v1, v2)):
+            self.part.halo_exchange(v)
+            self.ops.spmv(k_vals, v, self.q, self.owned, self.en[i:i + 1])
+        self.part.all_reduce(self.en)
+        return self.en

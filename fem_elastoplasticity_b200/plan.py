@@ -203,6 +203,12 @@ class FemPlan:
         call("fem_energy_norms", self._h, _ptr(k_vals), _ptr(v0), _ptr(v1), _ptr(v2), _ptr(work), _ptr(out), _stream())
         return out
 
+    def transform(self, q_int, out=None):
+        q = self._f64(q_int, (self.n_int,))
+        out = self.empty(self.n_n) if out is None else out
+        call("fem_transform", self._h, _ptr(q), _ptr(out), _stream())
+        return out
+
     # -- host views (façade / tests) -------------------------------------------------------------
     def pattern_host(self):
         return self.row_ptr.cpu().numpy().copy(), self.col_idx.cpu().numpy().copy()
@@ -211,6 +217,13 @@ class FemPlan:
         import scipy.sparse as sp
         rp, ci = self.pattern_host()
         return sp.csr_matrix((k_vals.detach().cpu().numpy(), ci, rp), shape=(self.n_dof, self.n_dof))
+
+
+def axpby(a, x, b, y, out=None):
+    """out = a*x + b*y on the device (fem_vec_axpby)."""
+    out = torch.empty_like(x) if out is None else out
+    call("fem_vec_axpby", x.numel(), float(a), _ptr(x), float(b), _ptr(y), _ptr(out), _stream())
+    return out
 
 
 def dp_return_map(e, ep_prev, shear, bulk, eta, c, apply_plastic_strain=False, e0=None, want_lambda=False,

@@ -168,7 +168,9 @@ def construct_constitutive_problem(e, *args, apply_plastic_strain=False):
     ind_p = r["ind_p"].cpu().numpy().astype(bool)
     lam = r["lambda"].cpu().numpy().reshape(1, -1)
     ep = r["ep"].cpu().numpy()
-    if apply_plastic_strain and ep_prev is not None:
+    if e0 is not None and counts.sum() == 0:
+        ep = np.zeros_like(ep)              # tsx early-out (tsx-tunnel/pythonFEM.py:1101-1103): ep_prev is ignored
+    elif apply_plastic_strain and ep_prev is not None:
         ep_prev[...] = ep                   # the reference returns ep_prev itself, mutated
         ep = ep_prev
     out = {'s': r["s"].cpu().numpy(), 'ds': r["ds"].cpu().numpy(), 'ind_p': ind_p,

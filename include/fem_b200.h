@@ -140,6 +140,13 @@ int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const
 int fem_energy_norms(const fem_plan* plan, const double* K_vals, const double* v0, const double* v1, const double* v2,
                      double* work, double* out, fem_stream stream);
 
+/* out = a*x + b*y (n doubles; out may alias x or y): the vector updates of the Newton / load-stepping glue
+ * (U_new = U_it + dU, :1069; U_it = d_zeta*(U-U_old)/d_zeta_old + U, :1120)                        */
+int fem_vec_axpby(int64_t n, double a, const double* x, double b, const double* y, double* out, fem_stream stream);
+/* transform(): integration-point values -> nodal weighted averages, q_node[n] = sum_g w_g q_g / sum_g w_g over the
+ * points of the elements around node n (Plasticity2D_DP/pythonFEM.py:760-816)                      */
+int fem_transform(const fem_plan* plan, const double* q_int, double* q_node, fem_stream stream);
+
 /* launch-shape knobs for benchmarking ("return_map_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm");
  * value 0 restores the default.  Results never depend on them.                                     */
 int fem_set_tuning(const char* key, int value);

@@ -113,11 +113,14 @@ def main():
         r = rp.construct_constitutive_problem(E.copy(), Ep.copy(), G, Kb, eta, c, apply)
         for k in ("s", "ds", "ind_p", "ep"):
             out[f"pl{int(apply)}_{k}"] = r[k]
-    e0 = 0.7 * np.array([[-1.04e-3], [-3.6e-4], [0], [-1.34e-3]])
-    r = rt.construct_constitutive_problem(E.copy(), e0, Ep.copy(), G, Kb, eta, c, True)
-    out["e0"] = e0
-    for k in ("s", "ds", "ind_p", "ep"):
-        out[f"tsx1_{k}"] = r[k]
+    # tsx signature: e0 small enough that points still yield (tsx1) and large enough that none does (tsx0: the
+    # early-out at tsx-tunnel/pythonFEM.py:1103 then returns ep = zeros even with apply_plastic_strain=True)
+    for tag, scale in (("tsx1", 0.05), ("tsx0", 0.7)):
+        e0 = scale * np.array([[-1.04e-3], [-3.6e-4], [0], [-1.34e-3]])
+        r = rt.construct_constitutive_problem(E.copy(), e0, Ep.copy(), G, Kb, eta, c, True)
+        out[f"{tag}_e0"] = e0
+        for k in ("s", "ds", "ind_p", "ep"):
+            out[f"{tag}_{k}"] = r[k]
     np.savez_compressed(os.path.join(OUT, "return_map.npz"), **out)
 
     # -- 5. Newton glue on footing L1 in a plastic state (Plasticity2D_DP:1043-1058) ------------

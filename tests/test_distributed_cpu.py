@@ -1,0 +1,142 @@
+"""Host-side logic of the multi-GPU path on CPU: strip partition, ghost layers, halo exchange and the
+placement of the scalar all-reduces in the PCG, run with world_size 2 and 3 over gloo.  The CUDA step
+kernels are replaced HERE (tests only) by a NumPy statement of the same five steps; the result must equal
+a single-domain sparse direct solve of K[Q,Q] x = b."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fem_oracle as fo
+
+
+class NumpyOps:
+    """Same contract as fem_elastoplasticity_b200.distributed.CudaOps (include/fem_b200.h: fem_pcg_*)."""
+
+    def __init__(self, K):
+        self.K, self.n = K.tocsr(), K.shape[0]
+
+    def new_vec(self, n=None):
+        return torch.zeros(self.n if n is None else n, dtype=torch.float64)
+
+    def jacobi(self, k, mask, out):
+        d = self.K.diagonal()
+        m = mask.numpy().astype(bool)
+        out.copy_(torch.as_tensor(np.where(m & (d != 0), 1.0 / np.where(d != 0, d, 1.0), 0.0)))
+
+    def pcg_init(self, rhs, kx0, mask, minv, r, p, scal):
+        scal.zero_()
+        b = rhs * mask
+        r.copy_(b if kx0 is None else (b - kx0 * mask))
+        p.copy_(minv * r)
+        scal[0], scal[1], scal[4] = torch.dot(r, p), torch.dot(r, r), torch.dot(b, b)
+
+    def spmv_dot(self, k, p, q, mask, scal, it):
+        scal[0 if it & 1 else 2] = 0.0
+        scal[1] = 0.0
+        q.copy_(torch.as_tensor(self.K @ p.numpy()) * mask)
+        scal[3] += torch.dot(p, q)
+
+    def update_xr(self, p, q, minv, x, r, scal, it):
+        old, new = (2, 0) if it & 1 else (0, 2)
+        alpha = scal[old] / scal[3] if scal[3] != 0 else 0.0
+        x += alpha * p
+        r -= alpha * q
+        scal[new] += torch.dot(r * minv, r)
+        scal[1] += torch.dot(r, r)
+
+    def update_p(self, r, minv, p, scal, it):
+        old, new = (2, 0) if it & 1 else (0, 2)
+        beta = scal[new] / scal[old] if scal[old] != 0 else 0.0
+        p.copy_(minv * r + beta * p)
+        scal[3] = 0.0
+
+    def spmv(self, k, x, y, mask, dot):
+        y.copy_(torch.as_tensor(self.K @ x.numpy()) * mask)
+        dot += torch.dot(x, y)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nx, ny, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fem_elastoplasticity_b200.distributed import DistributedPCG, StripPartition
+    part = StripPartition(nx, ny, rank, world, size_x=10.0, size_y=10.0 * world)
+    mesh = part.local_mesh("cpu")
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    elem, coord = mesh["elements"].numpy().astype(np.int64), mesh["coordinates"].numpy()
+    n_e = elem.shape[1]
+    G0, K0 = fo.footing_constants()[:2]
+    K = fo.elastic_stiffness(elem, coord, G0 * np.ones(n_e), K0 * np.ones(n_e), d1, d2, wf)[0]
+    q_local = mesh["Q"].t().reshape(-1).to(torch.uint8)
+    mask = q_local & part.owned_mask("cpu")
+    rng = np.random.default_rng(5)
+    b_global = rng.standard_normal(2 * (nx + 1) * (ny + 1))
+    lo = part.iy0 * part.row_dofs
+    rhs = torch.as_tensor(b_global[lo:lo + 2 * part.n_n_local].copy())
+    pcg = DistributedPCG(None, part, mask, ops=NumpyOps(K))
+    x, its = pcg.solve(None, rhs, rtol=1e-13, maxit=5000, check_every=10)
+    en = pcg.energy_norms(None, x.clone(), rhs.clone(), x.clone())
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), x=x.numpy(), lo=lo, its=its, en=en.numpy(),
+             own=np.array(part.owned_dof_range()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_partitioned_pcg_equals_single_domain(tmp_path, world):
+    nx, ny = 10, 12
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, nx, ny, str(tmp_path)), nprocs=world, join=True)
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    m = fo.square_mesh_p1(nx, ny, 10.0, 10.0 * world)
+    n_e = m["elements"].shape[1]
+    G0, K0 = fo.footing_constants()[:2]
+    K = fo.elastic_stiffness(m["elements"], m["coordinates"], G0 * np.ones(n_e), K0 * np.ones(n_e), d1, d2, wf)[0].tocsr()
+    qf = m["Q"].flatten(order="F")
+    b = np.random.default_rng(5).standard_normal(K.shape[0])
+    ref = np.zeros_like(b)
+    ref[qf] = spla.spsolve(K[qf][:, qf].tocsc(), b[qf])
+    got = np.full_like(b, np.nan)
+    for r in range(world):
+        d = np.load(tmp_path / f"r{r}.npz")
+        lo, (a, e) = int(d["lo"]), d["own"]
+        got[lo + a:lo + e] = d["x"][a:e]
+        # ghost rows hold the neighbour's converged values after the final halo exchange
+        np.testing.assert_allclose(d["x"], ref[lo:lo + d["x"].size], rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+        assert d["its"] > 0
+        np.testing.assert_allclose(d["en"][1], b @ (K @ b), rtol=1e-11)         # distributed energy product
+    assert not np.isnan(got).any()                                                # every DOF owned exactly once
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+
+
+def test_partition_bookkeeping():
+    from fem_elastoplasticity_b200.distributed import StripPartition
+    nx, ny, world = 7, 12, 4
+    owned = np.zeros(2 * (nx + 1) * (ny + 1), dtype=int)
+    n_e = 0
+    for r in range(world):
+        p = StripPartition(nx, ny, r, world)
+        lo = p.iy0 * p.row_dofs
+        a, e = p.owned_dof_range()
+        owned[lo + a:lo + e] += 1
+        n_e += p.n_e_owned
+        assert p.n_node_rows == p.ny_loc + 1 + (1 if p.has_upper else 0)
+    assert (owned == 1).all() and n_e == 2 * nx * ny
+    with pytest.raises(ValueError):
+        StripPartition(4, 10, 0, 3)

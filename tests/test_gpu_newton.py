@@ -1,0 +1,64 @@
+"""Newton-trace parity: the device-resident drivers against the reference driver's own log (footing L1)
+and against the oracle's restated tsx driver.  The reference solves each Newton system with a dense LU
+(Plasticity2D_DP/pythonFEM.py:1066); here it is Jacobi-PCG driven to rtol 1e-13."""
+import numpy as np
+import pytest
+
+from oracle import fem_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def test_footing_l1_trace_matches_reference_log(golden):
+    from fem_elastoplasticity_b200 import newton
+    g, m = golden("footing_l1_trace.npz"), golden("assembly_footing_p1_l1.npz")
+    mesh = {k: m[k] for k in ("coordinates", "elements", "Q", "dirichlet_nodes")}
+    out = newton.footing_driver(mesh)
+    crit = np.array([t[3] for t in out["trace"]])
+    ref = g["criterion"]
+    assert crit.shape == ref.shape == (109,), "same number of Newton iterations as the reference driver"
+    big = ref > 1e-9
+    np.testing.assert_allclose(crit[big], ref[big], rtol=1e-6)
+    assert np.all(crit[~big] < 1e-8)
+    assert out["steps"] - 1 == len(g["load_factor"]) == 16
+    # plastic point counts: the reference logs smooth/apex per return-map call
+    n_plast = [t[2] for t in out["trace"]]
+    it = iter(g["smooth_apex"].sum(axis=1))
+    assert all(any(c == r for r in it) for c in n_plast)
+    # displacement parity against the oracle's dense-solve driver
+    oref = fo.footing_driver(1)
+    err = np.abs(out["U"] - oref["U"]).max() / np.abs(oref["U"]).max()
+    print("footing L1 displacement error vs dense-solve oracle:", err)
+    assert err < 1e-9
+    np.testing.assert_allclose(out["Ep"], oref["Ep"], rtol=1e-6, atol=1e-9 * np.abs(oref["Ep"]).max())
+
+
+def test_tsx_driver_matches_oracle(golden):
+    from fem_elastoplasticity_b200 import newton
+    m = golden("assembly_tsx_p1.npz")
+    out = newton.tsx_driver(m["coordinates"], m["elements"])
+    oref = fo.tsx_driver(m["coordinates"], m["elements"])
+    assert out["steps"] == oref["steps"] == 17
+    assert [t[1] for t in out["trace"]] == [t[1] for t in oref["trace"]]          # Newton iteration indices
+    assert [t[2] for t in out["trace"]] == [t[2] for t in oref["trace"]]          # plastic point counts
+    err = np.abs(out["U"] - oref["U"]).max() / np.abs(oref["U"]).max()
+    print("tsx displacement error vs dense-solve oracle:", err)
+    assert err < 1e-10
+    assert np.array_equal(out["F0"], oref["F0"])                                   # B^T (w sigma0): bit-exact
+    # golden fq.csv: the converged residual on the free DOFs is ~0
+    g = golden("tsx_csv_golden.npz")
+    ns = out["solver"]
+    qf = out["Q"].flatten(order="F")
+    res = ns.F.cpu().numpy()[qf]
+    assert res.shape == g["fq"].shape
+    assert np.abs(res).max() < 1e-8 * np.abs(out["F0"]).max()
+
+
+def test_tangent_reference_mode_driver(golden):
+    """Same driver with K_tangent evaluated in the reference's own order (bit-identical matrices)."""
+    from fem_elastoplasticity_b200 import newton
+    m = golden("assembly_tsx_p1.npz")
+    a = newton.tsx_driver(m["coordinates"], m["elements"], tangent_mode="reference")
+    b = newton.tsx_driver(m["coordinates"], m["elements"], tangent_mode="direct")
+    assert a["steps"] == b["steps"] == 17
+    assert np.abs(a["U"] - b["U"]).max() <= 1e-10 * np.abs(a["U"]).max()
