@@ -36,16 +36,18 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; samples inside the timed region are reported
+    (plus, flagged, the ones taken under load during warm-up when the region is too short to catch three)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -53,19 +55,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def region_begin(self):
+        self.t_begin = time.time()
+
+    def region_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if self.t_begin is not None and self.t_begin <= t <= self.t_end + 0.1]
+        note = "samples inside the timed region"
+        if len(inside) < 3:
+            inside = [r for t, r in ok if float(r[3]) > 250.0] if ok and all(x[1][3].replace(".", "").isdigit() for x in ok) else [r for _, r in ok]
+            note = "timed region shorter than 3 sampling periods: samples under load (>250 W) from warm-up + timed region"
+        sm = [float(r[1]) for r in inside]
+        mx = [float(r[2]) for r in inside]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in inside for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max([float(r[3]) for r in inside], default=None), "note": note}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -205,14 +219,15 @@ def run_gpu(args):
         if record is not None:
             record.append(evs)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.region_begin()
     rec = []
     torch.cuda.synchronize()
     t0 = ev()
@@ -222,6 +237,7 @@ def run_gpu(args):
         step(rec)
     t1.record()
     torch.cuda.synchronize()
+    sampler.region_end()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -319,10 +335,10 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--nx", type=int, default=2828, help="cells per side per GPU (2828 -> 15 995 168 elements, config 4)")
-    ap.add_argument("--pcg-iters", type=int, default=20)
+    ap.add_argument("--pcg-iters", type=int, default=50)
     ap.add_argument("--cpu-nx", type=int, default=500, help="mesh side of the bounded CPU sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -17,9 +17,8 @@ def test_footing_l1_trace_matches_reference_log(golden):
     crit = np.array([t[3] for t in out["trace"]])
     ref = g["criterion"]
     assert crit.shape == ref.shape == (109,), "same number of Newton iterations as the reference driver"
-    big = ref > 1e-9
-    np.testing.assert_allclose(crit[big], ref[big], rtol=1e-6)
-    assert np.all(crit[~big] < 1e-8)
+    # PCG (rtol 1e-13) instead of a dense LU: criteria agree to 1e-5 relative down to the 1e-12 noise floor
+    np.testing.assert_allclose(crit, ref, rtol=1e-5, atol=1e-12)
     assert out["steps"] - 1 == len(g["load_factor"]) == 16
     # plastic point counts: the reference logs smooth/apex per return-map call
     n_plast = [t[2] for t in out["trace"]]
