@@ -188,6 +188,7 @@ def run_gpu(args):
     u = 1e-3 * torch.randn(P.n_dof, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
     mask = part.free_owned_mask(P, mesh)
     E = P.empty(3, P.n_int)
+    ep_old = torch.zeros((4, P.n_int), dtype=torch.float64, device=dev)
     rm = {}
     k_tan, F = P.empty(P.nnz), P.empty(P.n_dof)
     k_el = P.assemble_elastic(G, Kb)
@@ -206,7 +207,7 @@ def run_gpu(args):
         evs[0].record()
         P.strain(u, out=E)
         evs[1].record()
-        dp_return_map(Es, None, G, Kb, eta, c, want_ep=False, out=rm)
+        dp_return_map(Es, ep_old, G, Kb, eta, c, want_ep=False, out=rm)   # Ep_old is read (32 B/pt) as in the reference's Newton loop
         evs[2].record()
         P.assemble_tangent_force(rm["ds"], rm["s"], out_k=k_tan, out_f=F)
         evs[3].record()

@@ -35,6 +35,53 @@ constexpr int ACC_LD = 33;  // padded leading dimension: bank = (entry + lane) m
 
 enum { MODE_ELASTIC = 0, MODE_TANGENT = 1, MODE_TANGENT_REF = 2, MODE_FORCE_ONLY = 3 };
 
+// Per (node, element, quadrature point) terms shared by both assembly kernels: geometry rows d1/d2 of all
+// local nodes, t = (B^T D)[dof, 3g + c] for the two DOFs of local node `la`, and the internal-force update.
+template <int NP, int NQ, int MODE, bool FORCE>
+__device__ __forceinline__ void incidence_terms(const AsmArgs& A, int64_t g, int la, double (&d1)[NP], double (&d2)[NP],
+                                                double (&tx)[3], double (&ty)[3], double& f0, double& f1) {
+  const int64_t n_int = A.n_int;
+  const double w = A.weight[g];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    d1[p] = A.dphi1[(int64_t)p * n_int + g];
+    d2[p] = A.dphi2[(int64_t)p * n_int + g];
+  }
+  double d1a = d1[0], d2a = d2[0];
+#pragma unroll
+  for (int p = 1; p < NP; ++p)
+    if (p == la) {
+      d1a = d1[p];
+      d2a = d2[p];
+    }
+  if (FORCE) {  // F = B^T (w*s), csc_matvec order: strain rows 3g, 3g+1, 3g+2   (:1058)
+    const double ws0 = w * A.S[g], ws1 = w * A.S[n_int + g], ws2 = w * A.S[2 * n_int + g];
+    f0 = (f0 + d1a * ws0) + d2a * ws2;
+    f1 = (f1 + d2a * ws1) + d1a * ws2;
+  }
+  if (MODE == MODE_FORCE_ONLY) return;
+  double D[9];  // D[r + 3c]
+  if (MODE == MODE_ELASTIC) {            // vd = (2*dev*G + vol*K) * (1*w)        (:582,591)
+    const double G = A.shear[g], Kb = A.bulk[g];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) D[k] = (A.dev2[k] * G + A.vol[k] * Kb) * w;
+  } else if (MODE == MODE_TANGENT) {     // vD = w * ds                            (:1047)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g];
+  } else {                               // D_p - D_elast                          (:1050)
+    const double G = A.shear[g], Kb = A.bulk[g];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g] - (A.dev2[k] * G + A.vol[k] * Kb) * w;
+  }
+  // B columns of node la: x-dof (d1,0,d2), y-dof (0,d2,d1)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    tx[c] = d1a * D[3 * c] + d2a * D[2 + 3 * c];
+    ty[c] = d2a * D[1 + 3 * c] + d1a * D[2 + 3 * c];
+  }
+}
+
+// ---- variant A: accumulators in warp-private shared memory (any node degree) ---------------------
 template <int NP, int NQ, int MODE, bool FORCE>
 __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
   extern __shared__ double smem[];
@@ -54,7 +101,6 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
     for (int k = 0; k < 4 * deg; ++k) acc[k * ACC_LD + lane] = 0.0;
   const int64_t sbase = A.slice_ptr[slice];
   const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
-  const int64_t n_int = A.n_int;
   double f0 = 0.0, f1 = 0.0;
   for (int i = 0; i < width; ++i) {
     const int64_t at = sbase + (int64_t)i * 32 + lane;
@@ -67,47 +113,9 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
     for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
 #pragma unroll 1
     for (int q = 0; q < NQ; ++q) {
-      const int64_t g = e * NQ + q;
-      const double w = A.weight[g];
-      double d1[NP], d2[NP];
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        d1[p] = A.dphi1[(int64_t)p * n_int + g];
-        d2[p] = A.dphi2[(int64_t)p * n_int + g];
-      }
-      double d1a = d1[0], d2a = d2[0];
-#pragma unroll
-      for (int p = 1; p < NP; ++p)
-        if (p == la) {
-          d1a = d1[p];
-          d2a = d2[p];
-        }
-      if (FORCE) {  // F = B^T (w*s), csc_matvec order: strain rows 3g, 3g+1, 3g+2   (:1058)
-        const double ws0 = w * A.S[g], ws1 = w * A.S[n_int + g], ws2 = w * A.S[2 * n_int + g];
-        f0 = (f0 + d1a * ws0) + d2a * ws2;
-        f1 = (f1 + d2a * ws1) + d1a * ws2;
-      }
+      double d1[NP], d2[NP], tx[3], ty[3];
+      incidence_terms<NP, NQ, MODE, FORCE>(A, e * NQ + q, la, d1, d2, tx, ty, f0, f1);
       if (MODE == MODE_FORCE_ONLY) continue;
-      double D[9];  // D[r + 3c]
-      if (MODE == MODE_ELASTIC) {            // vd = (2*dev*G + vol*K) * (1*w)        (:582,591)
-        const double G = A.shear[g], Kb = A.bulk[g];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) D[k] = (A.dev2[k] * G + A.vol[k] * Kb) * w;
-      } else if (MODE == MODE_TANGENT) {     // vD = w * ds                            (:1047)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g];
-      } else {                               // D_p - D_elast                          (:1050)
-        const double G = A.shear[g], Kb = A.bulk[g];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g] - (A.dev2[k] * G + A.vol[k] * Kb) * w;
-      }
-      // t = (B^T D)[dof, 3g + c]; B columns of node la: x-dof (d1,0,d2), y-dof (0,d2,d1)
-      double tx[3], ty[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        tx[c] = d1a * D[3 * c] + d2a * D[2 + 3 * c];
-        ty[c] = d2a * D[1 + 3 * c] + d1a * D[2 + 3 * c];
-      }
 #pragma unroll
       for (int lb = 0; lb < NP; ++lb) {
         const int byte = lb + 1;
@@ -135,6 +143,88 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
       __stcs(A.K_vals + bt + l, v);
     }
   }
+}
+
+// ---- variant B: accumulators in registers (node degree <= MAXDEG) ---------------------------------
+// The slot a contribution goes to is data (position of the neighbour in the node's sorted list), so the
+// 4*MAXDEG accumulators are addressed through a `switch`: every case touches compile-time register names.
+// On structured meshes all lanes of a warp take the same case (same local topology) so the branch is
+// warp-uniform; on irregular meshes the cases serialise but stay correct.  No shared memory: the whole
+// 228 KB stay L1, which is what serves the re-reads of an element's DS/dphi by its three nodes.
+template <int NP, int NQ, int MODE, bool FORCE, int MAXDEG>
+__global__ void __launch_bounds__(128) assemble_rows_reg_kernel(const AsmArgs A) {
+  constexpr int MW = (NP + 1 + 3) / 4;
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slice = a >> 5;
+  if (slice >= A.n_slices) return;
+  const int lane = threadIdx.x & 31;
+  int deg = 0;
+  int64_t base = 0;
+  if (a < A.n_n) {
+    const int nb = A.nbr_ptr[a];
+    deg = A.nbr_ptr[a + 1] - nb;
+    base = 4 * (int64_t)nb;
+  }
+  double acc[MAXDEG][4];
+#pragma unroll
+  for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+  const int64_t sbase = A.slice_ptr[slice];
+  const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
+  double f0 = 0.0, f1 = 0.0;
+  for (int i = 0; i < width; ++i) {
+    const int64_t at = sbase + (int64_t)i * 32 + lane;
+    const uint32_t key = __ldcs(A.inc_key + at);
+    if (key == FEM_INVALID_KEY) continue;
+    const int64_t e = key >> 3;
+    const int la = key & 7;
+    uint32_t meta[MW];
+#pragma unroll
+    for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
+#pragma unroll 1
+    for (int q = 0; q < NQ; ++q) {
+      double d1[NP], d2[NP], tx[3], ty[3];
+      incidence_terms<NP, NQ, MODE, FORCE>(A, e * NQ + q, la, d1, d2, tx, ty, f0, f1);
+#pragma unroll
+      for (int lb = 0; lb < NP; ++lb) {
+        const int byte = lb + 1;
+        const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
+        const double b1 = d1[lb], b2 = d2[lb];
+        const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
+        const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
+#define FEM_UPD(J)                               \
+  case J:                                        \
+    if (J < MAXDEG) {                            \
+      acc[J < MAXDEG ? J : 0][0] = (acc[J < MAXDEG ? J : 0][0] + p00) + p01; \
+      acc[J < MAXDEG ? J : 0][1] = (acc[J < MAXDEG ? J : 0][1] + p10) + p11; \
+      acc[J < MAXDEG ? J : 0][2] = (acc[J < MAXDEG ? J : 0][2] + p20) + p21; \
+      acc[J < MAXDEG ? J : 0][3] = (acc[J < MAXDEG ? J : 0][3] + p30) + p31; \
+    }                                            \
+    break;
+        switch (slot) {
+          FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
+          FEM_UPD(8) FEM_UPD(9) FEM_UPD(10) FEM_UPD(11) FEM_UPD(12) FEM_UPD(13) FEM_UPD(14) FEM_UPD(15)
+          default: break;
+        }
+#undef FEM_UPD
+      }
+    }
+  }
+  if (a >= A.n_n) return;
+  if (FORCE) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+  double2* row0 = reinterpret_cast<double2*>(A.K_vals + base);
+  double2* row1 = row0 + deg;
+#pragma unroll
+  for (int j = 0; j < MAXDEG; ++j)
+    if (j < deg) {
+      double2 v0 = make_double2(acc[j][0], acc[j][1]), v1 = make_double2(acc[j][2], acc[j][3]);
+      if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction
+        const double2 k0 = reinterpret_cast<const double2*>(A.Kel + base)[j];
+        const double2 k1 = reinterpret_cast<const double2*>(A.Kel + base)[deg + j];
+        v0.x = k0.x + v0.x; v0.y = k0.y + v0.y; v1.x = k1.x + v1.x; v1.y = k1.y + v1.y;
+      }
+      __stcs(row0 + j, v0);
+      __stcs(row1 + j, v1);
+    }
 }
 
 // host-formed constants, exactly as numpy does at Plasticity2D_DP/pythonFEM.py:579-582
@@ -174,6 +264,20 @@ extern "C" int fem_elastic_dmat(const fem_plan* P, const double* shear, const do
 
 template <int MODE, bool FORCE>
 static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
+  // variant B (register accumulators) for P1/Q1 meshes of bounded valence; variant A (shared memory) otherwise
+  const int variant = g_fem_tuning.assemble_variant;
+  if (MODE != MODE_FORCE_ONLY && variant != 1) {
+    const unsigned blocks = (unsigned)fem_div_up(P->n_slices * 32, 128);
+    bool done = true;
+    if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 8) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8><<<blocks, 128, 0, st>>>(A);
+    else if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 12) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
+    else if (P->n_p == 4 && P->n_q == 4 && P->max_degree <= 12) assemble_rows_reg_kernel<4, 4, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
+    else done = false;
+    if (done) {
+      FEM_CUDA_CHECK(cudaGetLastError());
+      return FEM_OK;
+    }
+  }
   const int warps = (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= 4) ? g_fem_tuning.assemble_warps : 4;
   int acc_rows = (MODE == MODE_FORCE_ONLY) ? 0 : 4 * P->max_degree;
   A.acc_rows = acc_rows;

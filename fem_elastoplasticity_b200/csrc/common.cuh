@@ -21,6 +21,8 @@ struct FemTuning {
   int assemble_warps;      // warps per block of the assembly kernel (0 = 4)
   int spmv_group;          // lanes per node in the SpMV (0 = by degree)
   int spmv_blocks_per_sm;  // 0 = 32
+  int assemble_variant;    // 0 auto, 1 shared-memory accumulators, 2 register accumulators when possible
+  int spmv_unroll;         // nodes per lane group in flight (0 = default)
 };
 extern FemTuning g_fem_tuning;
 

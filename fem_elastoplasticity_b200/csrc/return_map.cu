@@ -201,8 +201,8 @@ extern "C" int fem_dp_return_map(int64_t n_int, const double* E, const double* h
                     aligned16(c) && aligned16(S) && aligned16(DS) && aligned16(Ep_prev) && aligned16(lambda) &&
                     aligned16(Ep_out) && ((reinterpret_cast<uintptr_t>(ind_p) & 1u) == 0);
   int variant = g_fem_tuning.return_map_variant;
-  if (variant < 1 || variant > 3) variant = 2;
-  if (!vec2) variant = 1;
+  if (variant < 1 || variant > 6) variant = 2;
+  if (!vec2 && variant != 4 && variant != 5) variant = 1;
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
   const int64_t cap = (int64_t)sms * 8 * 64;  // grid-stride beyond that
 #define RM_LAUNCH(V, T, MB, N)                                                                                     \
@@ -214,7 +214,10 @@ extern "C" int fem_dp_return_map(int64_t n_int, const double* E, const double* h
   } while (0)
   if (variant == 1) RM_LAUNCH(1, 256, 2, n_int);
   else if (variant == 2) RM_LAUNCH(2, 128, 3, n_int / 2);
-  else RM_LAUNCH(2, 256, 1, n_int / 2);
+  else if (variant == 3) RM_LAUNCH(2, 256, 1, n_int / 2);
+  else if (variant == 4) RM_LAUNCH(1, 128, 4, n_int);
+  else if (variant == 5) RM_LAUNCH(1, 128, 6, n_int);
+  else RM_LAUNCH(2, 64, 6, n_int / 2);
 #undef RM_LAUNCH
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;

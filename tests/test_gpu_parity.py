@@ -275,3 +275,27 @@ def test_large_mesh_properties(fem):
     F = P.internal_force(S).reshape(-1, 2)
     interior = (m["coordinates"][0] > 0) & (m["coordinates"][0] < 10) & (m["coordinates"][1] > 0) & (m["coordinates"][1] < 10)
     assert F[interior].abs().max().item() <= 1e-12
+
+
+def test_assembly_variants_agree_bitwise(fem, golden):
+    """Shared-memory and register accumulators run the same arithmetic in the same order."""
+    from fem_elastoplasticity_b200 import _lib
+    g, m = golden("newton_glue_footing_l1.npz"), golden("assembly_footing_p1_l1.npz")
+    d1, d2, wf = tables(fo.ElementType.P1)
+    n_e = m["elements"].shape[1]
+    G0, K0 = fo.footing_constants()[:2]
+    G, Kb = G0 * np.ones(n_e), K0 * np.ones(n_e)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    res = {}
+    try:
+        for v in (1, 2):
+            _lib.call("fem_set_tuning", b"assemble_variant", v)
+            kel = P.assemble_elastic(G, Kb)
+            kt, F = P.assemble_tangent_force(g["ds"], g["s"])
+            ktr = P.assemble_tangent_ref(g["ds"], G, Kb, kel)
+            res[v] = [t.cpu().numpy() for t in (kel, kt, F, ktr)]
+    finally:
+        _lib.call("fem_set_tuning", b"assemble_variant", 0)
+    for a, b in zip(res[1], res[2]):
+        assert np.array_equal(a, b)
+    assert_csr_bits(P.to_scipy_csr(fem["torch"].as_tensor(res[2][3]).cuda()), csr_from(g, "Kt"))
