@@ -35,43 +35,69 @@ constexpr int ACC_LD = 33;  // padded leading dimension: bank = (entry + lane) m
 
 enum { MODE_ELASTIC = 0, MODE_TANGENT = 1, MODE_TANGENT_REF = 2, MODE_FORCE_ONLY = 3 };
 
-// Per (node, element, quadrature point) terms shared by both assembly kernels: geometry rows d1/d2 of all
-// local nodes, t = (B^T D)[dof, 3g + c] for the two DOFs of local node `la`, and the internal-force update.
-template <int NP, int NQ, int MODE, bool FORCE>
-__device__ __forceinline__ void incidence_terms(const AsmArgs& A, int64_t g, int la, double (&d1)[NP], double (&d2)[NP],
-                                                double (&tx)[3], double (&ty)[3], double& f0, double& f1) {
+// Per (element, quadrature point) data and the terms both assembly kernels derive from it.
+template <int NP, int MODE, bool FORCE>
+struct PointData {
+  double w, d1[NP], d2[NP];
+  double raw[MODE == MODE_ELASTIC ? 2 : (MODE == MODE_TANGENT ? 9 : (MODE == MODE_TANGENT_REF ? 11 : 1))];
+  double s[FORCE ? 3 : 1];
+};
+
+template <int NP, int MODE, bool FORCE>
+__device__ __forceinline__ void load_point(const AsmArgs& A, int64_t g, PointData<NP, MODE, FORCE>& P) {
   const int64_t n_int = A.n_int;
-  const double w = A.weight[g];
+  P.w = A.weight[g];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    d1[p] = A.dphi1[(int64_t)p * n_int + g];
-    d2[p] = A.dphi2[(int64_t)p * n_int + g];
+    P.d1[p] = A.dphi1[(int64_t)p * n_int + g];
+    P.d2[p] = A.dphi2[(int64_t)p * n_int + g];
   }
-  double d1a = d1[0], d2a = d2[0];
+  if (MODE == MODE_ELASTIC) {
+    P.raw[0] = A.shear[g];
+    P.raw[1] = A.bulk[g];
+  } else if (MODE == MODE_TANGENT || MODE == MODE_TANGENT_REF) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) P.raw[k] = A.DS[(int64_t)k * n_int + g];
+    if (MODE == MODE_TANGENT_REF) {
+      P.raw[9] = A.shear[g];
+      P.raw[10] = A.bulk[g];
+    }
+  }
+  if (FORCE) {
+    P.s[0] = A.S[g];
+    P.s[1] = A.S[n_int + g];
+    P.s[2] = A.S[2 * n_int + g];
+  }
+}
+
+// t = (B^T D)[dof, 3g + c] for the two DOFs of local node `la`, and the internal-force update.
+template <int NP, int MODE, bool FORCE>
+__device__ __forceinline__ void point_terms(const AsmArgs& A, const PointData<NP, MODE, FORCE>& P, int la, double (&tx)[3],
+                                            double (&ty)[3], double& f0, double& f1) {
+  const double w = P.w;
+  double d1a = P.d1[0], d2a = P.d2[0];
 #pragma unroll
   for (int p = 1; p < NP; ++p)
     if (p == la) {
-      d1a = d1[p];
-      d2a = d2[p];
+      d1a = P.d1[p];
+      d2a = P.d2[p];
     }
   if (FORCE) {  // F = B^T (w*s), csc_matvec order: strain rows 3g, 3g+1, 3g+2   (:1058)
-    const double ws0 = w * A.S[g], ws1 = w * A.S[n_int + g], ws2 = w * A.S[2 * n_int + g];
+    const double ws0 = w * P.s[0], ws1 = w * P.s[1], ws2 = w * P.s[2];
     f0 = (f0 + d1a * ws0) + d2a * ws2;
     f1 = (f1 + d2a * ws1) + d1a * ws2;
   }
   if (MODE == MODE_FORCE_ONLY) return;
   double D[9];  // D[r + 3c]
   if (MODE == MODE_ELASTIC) {            // vd = (2*dev*G + vol*K) * (1*w)        (:582,591)
-    const double G = A.shear[g], Kb = A.bulk[g];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) D[k] = (A.dev2[k] * G + A.vol[k] * Kb) * w;
+    for (int k = 0; k < 9; ++k) D[k] = (A.dev2[k] * P.raw[0] + A.vol[k] * P.raw[1]) * w;
   } else if (MODE == MODE_TANGENT) {     // vD = w * ds                            (:1047)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g];
+    for (int k = 0; k < 9; ++k) D[k] = w * P.raw[k];
   } else {                               // D_p - D_elast                          (:1050)
-    const double G = A.shear[g], Kb = A.bulk[g];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) D[k] = w * A.DS[(int64_t)k * n_int + g] - (A.dev2[k] * G + A.vol[k] * Kb) * w;
+    for (int k = 0; k < 9; ++k) D[k] = w * P.raw[k] - (A.dev2[k] * P.raw[MODE == MODE_TANGENT_REF ? 9 : 0] + A.vol[k] * P.raw[MODE == MODE_TANGENT_REF ? 10 : 0]) * w;
   }
   // B columns of node la: x-dof (d1,0,d2), y-dof (0,d2,d1)
 #pragma unroll
@@ -113,8 +139,10 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
     for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
 #pragma unroll 1
     for (int q = 0; q < NQ; ++q) {
-      double d1[NP], d2[NP], tx[3], ty[3];
-      incidence_terms<NP, NQ, MODE, FORCE>(A, e * NQ + q, la, d1, d2, tx, ty, f0, f1);
+      double tx[3], ty[3];
+      PointData<NP, MODE, FORCE> pd;
+      load_point<NP, MODE, FORCE>(A, e * NQ + q, pd);
+      point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
       if (MODE == MODE_FORCE_ONLY) continue;
 #pragma unroll
       for (int lb = 0; lb < NP; ++lb) {
@@ -122,7 +150,7 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
         const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
         double* r0 = acc + (2 * slot) * ACC_LD + lane;
         double* r1 = acc + (2 * deg + 2 * slot) * ACC_LD + lane;
-        const double b1 = d1[lb], b2 = d2[lb];
+        const double b1 = pd.d1[lb], b2 = pd.d2[lb];
         r0[0] = (r0[0] + tx[0] * b1) + tx[2] * b2;            // K[2a  , 2b  ]
         r0[ACC_LD] = (r0[ACC_LD] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
         r1[0] = (r1[0] + ty[0] * b1) + ty[2] * b2;            // K[2a+1, 2b  ]
@@ -151,8 +179,8 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
 // On structured meshes all lanes of a warp take the same case (same local topology) so the branch is
 // warp-uniform; on irregular meshes the cases serialise but stay correct.  No shared memory: the whole
 // 228 KB stay L1, which is what serves the re-reads of an element's DS/dphi by its three nodes.
-template <int NP, int NQ, int MODE, bool FORCE, int MAXDEG>
-__global__ void __launch_bounds__(128) assemble_rows_reg_kernel(const AsmArgs A) {
+template <int NP, int NQ, int MODE, bool FORCE, int MAXDEG, bool PIPE, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmArgs A) {
   constexpr int MW = (NP + 1 + 3) / 4;
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t slice = a >> 5;
@@ -171,26 +199,54 @@ __global__ void __launch_bounds__(128) assemble_rows_reg_kernel(const AsmArgs A)
   const int64_t sbase = A.slice_ptr[slice];
   const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
   double f0 = 0.0, f1 = 0.0;
-  for (int i = 0; i < width; ++i) {
-    const int64_t at = sbase + (int64_t)i * 32 + lane;
-    const uint32_t key = __ldcs(A.inc_key + at);
-    if (key == FEM_INVALID_KEY) continue;
-    const int64_t e = key >> 3;
-    const int la = key & 7;
-    uint32_t meta[MW];
+  // Software pipeline: the incidence keys/metadata of a whole chunk are fetched up front (one latency instead
+  // of one per incidence) and the element data of incidence i+1 is in flight while incidence i is accumulated.
+  constexpr int CH = 8;
+  using PD = PointData<NP, MODE, FORCE>;
+  for (int c0 = 0; c0 < width; c0 += CH) {
+    uint32_t keys[CH], metas[CH][MW];
 #pragma unroll
-    for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
+    for (int i = 0; i < CH; ++i) {
+      keys[i] = FEM_INVALID_KEY;
+      if (c0 + i < width) {
+        const int64_t at = sbase + (int64_t)(c0 + i) * 32 + lane;
+        keys[i] = __ldcs(A.inc_key + at);
+#pragma unroll
+        for (int w = 0; w < MW; ++w) metas[i][w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
+      }
+    }
+    PD cur, nxt;
+    if (PIPE && keys[0] != FEM_INVALID_KEY) load_point<NP, MODE, FORCE>(A, (int64_t)(keys[0] >> 3) * NQ, cur);
+    const int n_it = (width - c0) < CH ? (width - c0) : CH;
 #pragma unroll 1
-    for (int q = 0; q < NQ; ++q) {
-      double d1[NP], d2[NP], tx[3], ty[3];
-      incidence_terms<NP, NQ, MODE, FORCE>(A, e * NQ + q, la, d1, d2, tx, ty, f0, f1);
+    for (int i = 0; i < n_it; ++i) {  // rolled: keys[0] is the current incidence, keys[1] the next (register queue)
+      const uint32_t key = keys[0];
+      const bool valid = key != FEM_INVALID_KEY;
+      const int64_t e = key >> 3;
+      const int la = key & 7;
+      uint32_t meta[MW];
 #pragma unroll
-      for (int lb = 0; lb < NP; ++lb) {
-        const int byte = lb + 1;
-        const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
-        const double b1 = d1[lb], b2 = d2[lb];
-        const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
-        const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
+      for (int w = 0; w < MW; ++w) meta[w] = metas[0][w];
+#pragma unroll 1
+      for (int q = 0; q < NQ; ++q) {
+        // prefetch the next point: next quadrature point of this element, else the first of the next incidence
+        if (!PIPE) {
+          if (valid) load_point<NP, MODE, FORCE>(A, e * NQ + q, cur);
+        } else if (q + 1 < NQ) {
+          if (valid) load_point<NP, MODE, FORCE>(A, e * NQ + q + 1, nxt);
+        } else if (i + 1 < n_it && keys[1] != FEM_INVALID_KEY) {
+          load_point<NP, MODE, FORCE>(A, (int64_t)(keys[1] >> 3) * NQ, nxt);
+        }
+        if (valid) {
+          double tx[3], ty[3];
+          point_terms<NP, MODE, FORCE>(A, cur, la, tx, ty, f0, f1);
+#pragma unroll
+          for (int lb = 0; lb < NP; ++lb) {
+            const int byte = lb + 1;
+            const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
+            const double b1 = cur.d1[lb], b2 = cur.d2[lb];
+            const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
+            const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
 #define FEM_UPD(J)                               \
   case J:                                        \
     if (J < MAXDEG) {                            \
@@ -200,12 +256,21 @@ __global__ void __launch_bounds__(128) assemble_rows_reg_kernel(const AsmArgs A)
       acc[J < MAXDEG ? J : 0][3] = (acc[J < MAXDEG ? J : 0][3] + p30) + p31; \
     }                                            \
     break;
-        switch (slot) {
-          FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
-          FEM_UPD(8) FEM_UPD(9) FEM_UPD(10) FEM_UPD(11) FEM_UPD(12) FEM_UPD(13) FEM_UPD(14) FEM_UPD(15)
-          default: break;
-        }
+            switch (slot) {
+              FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
+              FEM_UPD(8) FEM_UPD(9) FEM_UPD(10) FEM_UPD(11) FEM_UPD(12) FEM_UPD(13) FEM_UPD(14) FEM_UPD(15)
+              default: break;
+            }
 #undef FEM_UPD
+          }
+        }
+        if (PIPE) cur = nxt;
+      }
+#pragma unroll
+      for (int k = 0; k + 1 < CH; ++k) {  // shift the key queue
+        keys[k] = keys[k + 1];
+#pragma unroll
+        for (int w = 0; w < MW; ++w) metas[k][w] = metas[k + 1][w];
       }
     }
   }
@@ -269,9 +334,14 @@ static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   if (MODE != MODE_FORCE_ONLY && variant != 1) {
     const unsigned blocks = (unsigned)fem_div_up(P->n_slices * 32, 128);
     bool done = true;
-    if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 8) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8><<<blocks, 128, 0, st>>>(A);
-    else if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 12) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
-    else if (P->n_p == 4 && P->n_q == 4 && P->max_degree <= 12) assemble_rows_reg_kernel<4, 4, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
+    if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 8) {
+      // launch-shape variants of the P1 kernel (tuning knob assemble_variant: 2 = default unpipelined, 3/4 = data double-buffered with 2/3 blocks per SM)
+      if (variant == 3) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, true, 2><<<blocks, 128, 0, st>>>(A);
+      else if (variant == 4) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, true, 3><<<blocks, 128, 0, st>>>(A);
+      else assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, false, 1><<<blocks, 128, 0, st>>>(A);  // measured best (tools/tune.py)
+    }
+    else if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 12) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 12, false, 1><<<blocks, 128, 0, st>>>(A);
+    else if (P->n_p == 4 && P->n_q == 4 && P->max_degree <= 12) assemble_rows_reg_kernel<4, 4, MODE, FORCE, 12, false, 2><<<blocks, 128, 0, st>>>(A);
     else done = false;
     if (done) {
       FEM_CUDA_CHECK(cudaGetLastError());

@@ -201,7 +201,7 @@ extern "C" int fem_dp_return_map(int64_t n_int, const double* E, const double* h
                     aligned16(c) && aligned16(S) && aligned16(DS) && aligned16(Ep_prev) && aligned16(lambda) &&
                     aligned16(Ep_out) && ((reinterpret_cast<uintptr_t>(ind_p) & 1u) == 0);
   int variant = g_fem_tuning.return_map_variant;
-  if (variant < 1 || variant > 6) variant = 2;
+  if (variant < 1 || variant > 6) variant = 5;  // measured best at 16M points (tools/tune.py): 1 point/thread, 128 threads, 6 blocks/SM
   if (!vec2 && variant != 4 && variant != 5) variant = 1;
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counts);
   const int64_t cap = (int64_t)sms * 8 * 64;  // grid-stride beyond that

@@ -102,7 +102,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
   FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
   const int threads = 256;
-  int group = P->max_degree <= 4 ? 4 : (P->max_degree <= 12 ? 8 : 16);
+  int group = P->max_degree <= 8 ? 4 : (P->max_degree <= 16 ? 8 : 16);  // P1: 7 blocks per row pair -> 2 per lane
   if (g_fem_tuning.spmv_group == 4 || g_fem_tuning.spmv_group == 8 || g_fem_tuning.spmv_group == 16) group = g_fem_tuning.spmv_group;
   int unroll = g_fem_tuning.spmv_unroll;
   if (unroll != 1 && unroll != 2 && unroll != 4) unroll = 2;

@@ -288,7 +288,7 @@ def test_assembly_variants_agree_bitwise(fem, golden):
     P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
     res = {}
     try:
-        for v in (1, 2):
+        for v in (1, 2, 3, 4):
             _lib.call("fem_set_tuning", b"assemble_variant", v)
             kel = P.assemble_elastic(G, Kb)
             kt, F = P.assemble_tangent_force(g["ds"], g["s"])
@@ -296,6 +296,7 @@ def test_assembly_variants_agree_bitwise(fem, golden):
             res[v] = [t.cpu().numpy() for t in (kel, kt, F, ktr)]
     finally:
         _lib.call("fem_set_tuning", b"assemble_variant", 0)
-    for a, b in zip(res[1], res[2]):
-        assert np.array_equal(a, b)
+    for v in (2, 3, 4):
+        for a, b in zip(res[1], res[v]):
+            assert np.array_equal(a, b), v
     assert_csr_bits(P.to_scipy_csr(fem["torch"].as_tensor(res[2][3]).cuda()), csr_from(g, "Kt"))

@@ -52,7 +52,7 @@ def main():
     r = dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm)
     kel_ref = None
     k, F = P.empty(P.nnz), P.empty(P.n_dof)
-    for v, name in ((1, "smem"), (2, "reg")):
+    for v, name in ((1, "smem"), (2, "reg"), (3, "regpipe2"), (4, "regpipe3")):
         knob("assemble_variant", v)
         res[f"assemble_elastic_{name}_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
         kel = k.clone()
@@ -63,7 +63,7 @@ def main():
         if kel_ref is None:
             kel_ref, kt_ref, F_ref = kel, kt, F.clone()
         else:
-            res["reg_equals_smem_bits"] = bool(torch.equal(kel, kel_ref) and torch.equal(kt, kt_ref) and torch.equal(F, F_ref))
+            res[f"{name}_equals_smem_bits"] = bool(torch.equal(kel, kel_ref) and torch.equal(kt, kt_ref) and torch.equal(F, F_ref))
     knob("assemble_variant", 0)
     res["internal_force_ms"] = timeit(lambda: P.internal_force(r["s"], out=F))
     u = torch.randn(P.n_dof, dtype=torch.float64, device="cuda")
@@ -74,8 +74,8 @@ def main():
     dot = torch.zeros(1, dtype=torch.float64, device="cuda")
     y_ref = None
     for g in (4, 8):
-        for un in (1, 2, 4):
-            for bps in (16, 32, 64):
+        for un in (2, 4):
+            for bps in (8, 16, 32):
                 knob("spmv_group", g), knob("spmv_unroll", un), knob("spmv_blocks_per_sm", bps)
                 res[f"spmv_g{g}_u{un}_b{bps}_ms"] = timeit(lambda: P.spmv(kel_ref, u, mask=mask, out=y, dot=dot))
                 if y_ref is None:
