@@ -34,6 +34,7 @@ SIGNATURES = {
     "fem_plan_pattern": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)],
     "fem_plan_blocks": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)],
     "fem_plan_geometry": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "fem_plan_stage_info": [_vp, C.POINTER(_i32), C.POINTER(_i32)],
     "fem_plan_bytes": [_vp],
     "fem_elastic_dmat": [_vp, _vp, _vp, _vp, _vp],
     "fem_assemble_elastic": [_vp, _vp, _vp, _vp, _vp],

@@ -26,6 +26,11 @@ struct AsmArgs {
   const double* S;      // FORCE       [>=3][n_int]
   double* K_vals;
   double* F;
+  // TMA-staged variant
+  const int32_t* stage_runs;
+  const uint32_t* inc_stage;
+  const double* stage_src[20];  // SoA rows staged per slice: weight, dphi1[3], dphi2[3], mode inputs, S[3]
+  int stage_cap;
   int acc_rows;         // 4 * max_degree
   double dev2[9];       // 2*Dev (column-major) formed as numpy forms it (:579-582)
   double vol[9];
@@ -292,6 +297,183 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
     }
 }
 
+// ---- variant C: TMA-staged (P1, node degree <= 8) ---------------------------------------------------
+// The elements touched by the 32 nodes of a slice form a few runs of consecutive ids (plan: stage_runs).  One lane
+// brings every SoA row of those runs into warp-private shared memory with cp.async.bulk (TMA) completing on an
+// mbarrier: each element is fetched once per slice, fully coalesced, with ~20 KB in flight per warp regardless of
+// occupancy.  The accumulation then runs out of shared memory with exactly the arithmetic of variants A/B.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int MODE, bool FORCE>
+struct StageLayout {
+  static constexpr int NRAW = MODE == MODE_ELASTIC ? 2 : (MODE == MODE_TANGENT ? 9 : 11);
+  static constexpr int NARR = 7 + NRAW + (FORCE ? 3 : 0);
+};
+
+template <int MODE, bool FORCE, int MAXDEG>
+__global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A) {
+  constexpr int NP = 3;
+  using L = StageLayout<MODE, FORCE>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slice >= A.n_slices) return;  // warp-uniform; only warp-level synchronisation below
+  const int cap = A.stage_cap;
+  const size_t warp_bytes = (size_t)L::NARR * cap * sizeof(double) + 16;
+  double* buf = reinterpret_cast<double*>(smem_raw + warp * warp_bytes);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(buf + (size_t)L::NARR * cap);
+  const int32_t* runs = A.stage_runs + slice * (1 + 2 * FEM_STAGE_RMAX);
+  const int n_runs = runs[0];
+  int total = 0;
+  for (int r = 0; r < n_runs; ++r) total += runs[2 + 2 * r];
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (lane == 0 && total > 0) {
+    const uint32_t bar = smem_u32(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(L::NARR * total * 8)) : "memory");
+    int off = 0;
+    for (int r = 0; r < n_runs; ++r) {
+      const int start = runs[1 + 2 * r], len = runs[2 + 2 * r];
+#pragma unroll
+      for (int k = 0; k < L::NARR; ++k) {
+        const uint32_t dst = smem_u32(buf + (size_t)k * cap + off);
+        const double* src = A.stage_src[k] + start;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"((uint32_t)(len * 8)), "r"(bar)
+                     : "memory");
+      }
+      off += len;
+    }
+  }
+  // while the copies fly: node bookkeeping, incidence words, accumulator init
+  const int64_t a = slice * 32 + lane;
+  int deg = 0;
+  int64_t base = 0;
+  if (a < A.n_n) {
+    const int nb = A.nbr_ptr[a];
+    deg = A.nbr_ptr[a + 1] - nb;
+    base = 4 * (int64_t)nb;
+  }
+  const int64_t sbase = A.slice_ptr[slice];
+  const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
+  constexpr int CH = 8;  // plan guarantees width <= 8 when stage_ok
+  uint32_t words[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) words[i] = (i < width) ? __ldcs(A.inc_stage + sbase + (int64_t)i * 32 + lane) : 0u;
+  double acc[MAXDEG][4];
+#pragma unroll
+  for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+  double f0 = 0.0, f1 = 0.0;
+  if (total > 0) {
+    const uint32_t bar = smem_u32(mbar);
+    uint32_t ok = 0;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok)
+                   : "r"(bar), "r"(0)
+                   : "memory");
+    } while (!ok);
+  }
+#pragma unroll 1
+  for (int i = 0; i < width; ++i) {
+    const uint32_t word = words[0];
+#pragma unroll
+    for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
+    if (!(word & 0x80000000u)) continue;
+    const int li = word & 0xFF;
+    const int la = (word >> 8) & 3;
+    PointData<NP, MODE, FORCE> pd;
+    pd.w = buf[li];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      pd.d1[p] = buf[(size_t)(1 + p) * cap + li];
+      pd.d2[p] = buf[(size_t)(4 + p) * cap + li];
+    }
+#pragma unroll
+    for (int k = 0; k < L::NRAW; ++k) pd.raw[k] = buf[(size_t)(7 + k) * cap + li];
+    if (FORCE) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) pd.s[k] = buf[(size_t)(7 + L::NRAW + k) * cap + li];
+    }
+    double tx[3], ty[3];
+    point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
+#pragma unroll
+    for (int lb = 0; lb < NP; ++lb) {
+      const int slot = (word >> (10 + 4 * lb)) & 15;
+      const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+      const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
+      const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
+#define FEM_UPD(J)                               \
+  case J:                                        \
+    if (J < MAXDEG) {                            \
+      acc[J < MAXDEG ? J : 0][0] = (acc[J < MAXDEG ? J : 0][0] + p00) + p01; \
+      acc[J < MAXDEG ? J : 0][1] = (acc[J < MAXDEG ? J : 0][1] + p10) + p11; \
+      acc[J < MAXDEG ? J : 0][2] = (acc[J < MAXDEG ? J : 0][2] + p20) + p21; \
+      acc[J < MAXDEG ? J : 0][3] = (acc[J < MAXDEG ? J : 0][3] + p30) + p31; \
+    }                                            \
+    break;
+      switch (slot) {
+        FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
+        default: break;
+      }
+#undef FEM_UPD
+    }
+  }
+  if (a >= A.n_n) return;
+  if (FORCE) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+  double2* row0 = reinterpret_cast<double2*>(A.K_vals + base);
+  double2* row1 = row0 + deg;
+#pragma unroll
+  for (int j = 0; j < MAXDEG; ++j)
+    if (j < deg) {
+      double2 v0 = make_double2(acc[j][0], acc[j][1]), v1 = make_double2(acc[j][2], acc[j][3]);
+      if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction
+        const double2 k0 = reinterpret_cast<const double2*>(A.Kel + base)[j];
+        const double2 k1 = reinterpret_cast<const double2*>(A.Kel + base)[deg + j];
+        v0.x = k0.x + v0.x; v0.y = k0.y + v0.y; v1.x = k1.x + v1.x; v1.y = k1.y + v1.y;
+      }
+      __stcs(row0 + j, v0);
+      __stcs(row1 + j, v1);
+    }
+}
+
+template <int MODE, bool FORCE>
+static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
+  using L = StageLayout<MODE, FORCE>;
+  A.stage_runs = P->stage_runs;
+  A.inc_stage = P->inc_stage;
+  A.stage_cap = P->stage_cap;
+  int k = 0;
+  A.stage_src[k++] = P->weight;
+  for (int p = 0; p < 3; ++p) A.stage_src[k++] = P->dphi1 + (int64_t)p * P->n_int;
+  for (int p = 0; p < 3; ++p) A.stage_src[k++] = P->dphi2 + (int64_t)p * P->n_int;
+  if (MODE == MODE_ELASTIC) {
+    A.stage_src[k++] = A.shear;
+    A.stage_src[k++] = A.bulk;
+  } else {
+    for (int q = 0; q < 9; ++q) A.stage_src[k++] = A.DS + (int64_t)q * P->n_int;
+    if (MODE == MODE_TANGENT_REF) {
+      A.stage_src[k++] = A.shear;
+      A.stage_src[k++] = A.bulk;
+    }
+  }
+  if (FORCE)
+    for (int q = 0; q < 3; ++q) A.stage_src[k++] = A.S + (int64_t)q * P->n_int;
+  for (int i = 0; i < k; ++i)
+    if (reinterpret_cast<uintptr_t>(A.stage_src[i]) & 15u) return -1;  // bulk copies need 16-byte aligned rows: fall back
+  const int warps = 4;
+  const size_t smem = warps * ((size_t)L::NARR * P->stage_cap * sizeof(double) + 16);
+  if (smem > 227 * 1024) return -1;
+  auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
+  FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
 // host-formed constants, exactly as numpy does at Plasticity2D_DP/pythonFEM.py:579-582
 static void elastic_coeffs(double* dev2, double* vol) {
   const double iota[3] = {1.0, 1.0, 0.0};
@@ -331,6 +513,10 @@ template <int MODE, bool FORCE>
 static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   // variant B (register accumulators) for P1/Q1 meshes of bounded valence; variant A (shared memory) otherwise
   const int variant = g_fem_tuning.assemble_variant;
+  if (MODE != MODE_FORCE_ONLY && P->stage_ok && (variant == 0 || variant == 6)) {
+    const int rc = launch_assemble_tma<MODE == MODE_FORCE_ONLY ? MODE_TANGENT : MODE, FORCE>(P, A, st);
+    if (rc >= 0) return rc;  // -1: inputs not 16-byte aligned / too much shared memory -> register kernel
+  }
   if (MODE != MODE_FORCE_ONLY && variant != 1) {
     const unsigned blocks = (unsigned)fem_div_up(P->n_slices * 32, 128);
     bool done = true;

@@ -13,6 +13,8 @@
 #define FEM_MAX_NQ 9
 #define FEM_WARP 32
 #define FEM_INVALID_KEY 0xFFFFFFFFu
+#define FEM_STAGE_RMAX 4
+#define FEM_STAGE_CAP 192   // max staged elements per slice (li must fit 8 bits)
 
 void fem_set_error(const char* fmt, ...);
 
@@ -75,6 +77,11 @@ struct fem_plan {
   double* weight;  // [n_int]
   // scratch
   double* dscratch;  // small device scratch (8 doubles)
+  // TMA staging data of the P1 assembly kernel (valid when stage_ok): per 32-node slice the touched elements as
+  // <= FEM_STAGE_RMAX runs of consecutive ids (16-byte aligned), and per incidence its position in the staged buffer
+  int stage_ok, stage_cap;
+  int32_t* stage_runs;   // [n_slices][1 + 2*FEM_STAGE_RMAX]: count, then (start, length) pairs
+  uint32_t* inc_stage;   // [sell_entries]: li | la<<8 | slot0<<10 | slot1<<14 | slot2<<18 | valid<<31
   int64_t bytes;
 };
 

@@ -340,6 +340,96 @@ __global__ void __launch_bounds__(256) geometry_kernel(int64_t n_e, int64_t n_n,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Staging plan for the TMA assembly kernel (P1, node degree <= 8): the set of elements touched by the 32 nodes of a
+// slice, expressed as a few runs of consecutive element ids, so that each SoA array can be brought into shared
+// memory with one bulk copy per run.  Every lane of the warp builds the same run list redundantly (no divergence).
+// ------------------------------------------------------------------------------------------------
+__global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, const int64_t* __restrict__ slice_ptr,
+                            const uint32_t* __restrict__ inc_key, const uint32_t* __restrict__ inc_meta,
+                            int32_t* __restrict__ stage_runs, uint32_t* __restrict__ inc_stage, int* fail, int* cap_max) {
+  constexpr int RT = 8, W = 8;
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slice >= n_slices) return;
+  const int64_t sbase = slice_ptr[slice];
+  const int width = (int)((slice_ptr[slice + 1] - sbase) >> 5);
+  int32_t* out = stage_runs + slice * (1 + 2 * FEM_STAGE_RMAX);
+  if (width > W) {
+    if (lane == 0) { atomicAdd(fail, 1); out[0] = 0; }
+    return;
+  }
+  uint32_t keys[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) keys[i] = (i < width) ? inc_key[sbase + (int64_t)i * 32 + lane] : FEM_INVALID_KEY;
+  int rs[RT], re[RT];  // [start, end) sorted by start
+  int nr = 0;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (i >= width) break;
+    for (int t = 0; t < 32; ++t) {
+      const uint32_t k = __shfl_sync(0xffffffffu, keys[i], t);
+      if (k == FEM_INVALID_KEY) continue;
+      const int x = (int)(k >> 3);
+      bool done = false;
+      for (int r = 0; r < nr; ++r)
+        if (x >= rs[r] - 2 && x <= re[r] + 1) {  // inside, adjacent, or one element away (the gap is staged too)
+          if (x < rs[r]) rs[r] = x;
+          else if (x >= re[r]) re[r] = x + 1;
+          done = true;
+          break;
+        }
+      if (!done) {
+        if (nr == RT) { bad = true; continue; }
+        int pos = nr;
+        while (pos > 0 && rs[pos - 1] > x) { rs[pos] = rs[pos - 1]; re[pos] = re[pos - 1]; --pos; }
+        rs[pos] = x; re[pos] = x + 1;
+        ++nr;
+      }
+    }
+  }
+  // align to 16 bytes (even element ids) and merge runs that touch or overlap
+  for (int r = 0; r < nr; ++r) { rs[r] &= ~1; re[r] = (re[r] + 1) & ~1; if (re[r] > n_int) re[r] = (int)n_int; }
+  int m = 0;
+  for (int r = 0; r < nr; ++r) {
+    if (m > 0 && rs[r] <= re[m - 1] + 2) { if (re[r] > re[m - 1]) re[m - 1] = re[r]; }
+    else { rs[m] = rs[r]; re[m] = re[r]; ++m; }
+  }
+  nr = m;
+  int total = 0;
+  for (int r = 0; r < nr; ++r) total += re[r] - rs[r];
+  if (nr > FEM_STAGE_RMAX || total > FEM_STAGE_CAP) bad = true;
+  if (bad) {
+    if (lane == 0) { atomicAdd(fail, 1); out[0] = 0; }
+    return;
+  }
+  if (lane == 0) {
+    out[0] = nr;
+    for (int r = 0; r < nr; ++r) { out[1 + 2 * r] = rs[r]; out[2 + 2 * r] = re[r] - rs[r]; }
+    atomicMax(cap_max, total);
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    if (i >= width) break;
+    const int64_t at = sbase + (int64_t)i * 32 + lane;
+    uint32_t word = 0;
+    if (keys[i] != FEM_INVALID_KEY) {
+      const int x = (int)(keys[i] >> 3);
+      int off = 0, li = 0;
+      for (int r = 0; r < nr; ++r) {
+        if (x >= rs[r] && x < re[r]) li = off + x - rs[r];
+        off += re[r] - rs[r];
+      }
+      const uint32_t meta = inc_meta[at];  // la | pos0<<8 | pos1<<16 | pos2<<24
+      word = (uint32_t)li | ((meta & 3u) << 8) | (((meta >> 8) & 15u) << 10) | (((meta >> 16) & 15u) << 14) |
+             (((meta >> 24) & 15u) << 18) | 0x80000000u;
+    }
+    inc_stage[at] = word;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 static int dmalloc(fem_plan* p, T** ptr, int64_t count) {
@@ -457,6 +547,23 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     if ((rc = dmalloc(P, &P->weight, P->n_int)) != FEM_OK) break;
     if ((rc = dmalloc(P, &P->dscratch, 16)) != FEM_OK) break;
     if ((rc = launch_geometry(P, coord, flags + 3, st)) != FEM_OK) break;
+    // TMA staging plan (P1 meshes of bounded valence whose slices touch few runs of consecutive elements)
+    P->stage_ok = 0;
+    if (n_p == 3 && P->n_q == 1 && P->max_degree <= 8 && P->max_inc <= 8 && (P->n_int % 2) == 0) {
+      int* sflags = nullptr;  // [0] failed slices, [1] max staged elements
+      if (cudaMalloc(&sflags, 2 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc sflags"); break; }
+      cudaMemsetAsync(sflags, 0, 2 * sizeof(int), st);
+      if ((rc = dmalloc(P, &P->stage_runs, P->n_slices * (1 + 2 * FEM_STAGE_RMAX))) != FEM_OK) break;
+      if ((rc = dmalloc(P, &P->inc_stage, P->sell_entries)) != FEM_OK) break;
+      build_stage<<<(unsigned)((P->n_slices * 32 + threads - 1) / threads), threads, 0, st>>>(
+          n_n, P->n_slices, P->n_int, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_runs, P->inc_stage, sflags, sflags + 1);
+      int hs[2] = {1, 0};
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hs, sflags, sizeof(hs), cudaMemcpyDeviceToHost);
+      cudaFree(sflags);
+      P->stage_ok = (hs[0] == 0 && hs[1] > 0);
+      P->stage_cap = (hs[1] + 1) & ~1;
+    }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fem_set_error("plan build failed: %s", cudaGetErrorString(e)); rc = FEM_ERR_CUDA; break; }
     cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost);
@@ -516,6 +623,7 @@ extern "C" int fem_plan_create(int64_t n_n, int64_t n_e, int n_p, int n_q, const
 
 extern "C" int fem_plan_destroy(fem_plan* P) {
   if (!P) return FEM_OK;
+  cudaFree(P->stage_runs); cudaFree(P->inc_stage);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
   cudaFree(P->dphi1); cudaFree(P->dphi2); cudaFree(P->weight); cudaFree(P->dscratch);
@@ -553,6 +661,12 @@ extern "C" int fem_plan_geometry(const fem_plan* P, const double** dphi1, const 
   if (dphi1) *dphi1 = P->dphi1;
   if (dphi2) *dphi2 = P->dphi2;
   if (weight) *weight = P->weight;
+  return FEM_OK;
+}
+extern "C" int fem_plan_stage_info(const fem_plan* P, int* stage_ok, int* stage_cap) {
+  FEM_REQUIRE(P, "plan");
+  if (stage_ok) *stage_ok = P->stage_ok;
+  if (stage_cap) *stage_cap = P->stage_cap;
   return FEM_OK;
 }
 extern "C" int64_t fem_plan_bytes(const fem_plan* P) { return P ? P->bytes : 0; }

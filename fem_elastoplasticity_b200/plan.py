@@ -94,6 +94,12 @@ class FemPlan:
         self.weight = torch.as_tensor(_DevView(gw.value, (self.n_int,), "<f8"), device=self.device)
         self.bytes = int(_lib.load().fem_plan_bytes(self._h))
 
+    def stage_info(self):
+        """(stage_ok, staged elements per slice) of the TMA-staged assembly kernel."""
+        ok, cap = C.c_int(), C.c_int()
+        call("fem_plan_stage_info", self._h, C.byref(ok), C.byref(cap))
+        return int(ok.value), int(cap.value)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             for name in ("row_ptr", "col_idx", "nbr_ptr", "nbr_idx", "dphi1", "dphi2", "weight"):

@@ -42,7 +42,7 @@ def main():
     G, Kb, eta, c = meshgen.footing_materials(P.n_int)
     Es = meshgen.synthetic_strain(P.n_int)
     ep = torch.zeros((4, P.n_int), dtype=torch.float64, device="cuda")
-    out = {"n_e": P.n_e, "nnz": P.nnz, "n_dof": P.n_dof, "max_degree": P.max_degree}
+    out = {"n_e": P.n_e, "nnz": P.nnz, "n_dof": P.n_dof, "max_degree": P.max_degree, "stage": P.stage_info()}
     rm = {}
     res = {}
     for v in (1, 2, 3, 4, 5, 6):
@@ -52,7 +52,7 @@ def main():
     r = dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm)
     kel_ref = None
     k, F = P.empty(P.nnz), P.empty(P.n_dof)
-    for v, name in ((1, "smem"), (2, "reg"), (3, "regpipe2"), (4, "regpipe3")):
+    for v, name in ((1, "smem"), (2, "reg"), (6, "tma")):
         knob("assemble_variant", v)
         res[f"assemble_elastic_{name}_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
         kel = k.clone()
