@@ -27,10 +27,9 @@ struct AsmArgs {
   double* K_vals;
   double* F;
   // TMA-staged variant
-  const int32_t* stage_runs;
+  const int32_t* stage_box;
   const uint32_t* inc_stage;
-  const double* stage_src[20];  // SoA rows staged per slice: weight, dphi1[3], dphi2[3], mode inputs, S[3]
-  int stage_cap;
+  int boxw;
   int acc_rows;         // 4 * max_degree
   double dev2[9];       // 2*Dev (column-major) formed as numpy forms it (:579-582)
   double vol[9];
@@ -298,54 +297,84 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
 }
 
 // ---- variant C: TMA-staged (P1, node degree <= 8) ---------------------------------------------------
-// The elements touched by the 32 nodes of a slice form a few runs of consecutive ids (plan: stage_runs).  One lane
-// brings every SoA row of those runs into warp-private shared memory with cp.async.bulk (TMA) completing on an
-// mbarrier: each element is fetched once per slice, fully coalesced, with ~20 KB in flight per warp regardless of
-// occupancy.  The accumulation then runs out of shared memory with exactly the arithmetic of variants A/B.
+// The elements touched by the 32 nodes of a slice form (on structured meshes) two runs of consecutive ids, each covered
+// by one fixed-width box (plan: stage_box).  One lane brings the boxes into warp-private shared memory with 2-D TMA
+// tensor copies (cp.async.bulk.tensor.2d completing on an mbarrier): one copy per tensor and box - all 7 geometry rows,
+// all 9 DS rows, the 3 S rows - so 3 copies per box instead of 19 row copies (a 1-D bulk-copy version was TMA
+// issue-rate bound, ~50 cycles per copy per SM).  Each element is fetched once per slice, fully coalesced, with ~20 KB
+// in flight per warp regardless of occupancy; the accumulation then runs out of shared memory with exactly the
+// arithmetic of variants A/B.  Slices that need more than two boxes take the direct-load path of variant B.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct alignas(64) StageMaps {
+  CUtensorMap geom;  // [7][n_int]  weight, dphi1[3], dphi2[3]
+  CUtensorMap t0;    // MODE_ELASTIC: shear [1][n_int]; else DS [9][n_int]
+  CUtensorMap t1;    // MODE_ELASTIC: bulk;  MODE_TANGENT_REF: shear
+  CUtensorMap t2;    // MODE_TANGENT_REF: bulk
+  CUtensorMap s;     // FORCE: S rows 0..2 [3][n_int]
+};
+
+__host__ __device__ constexpr int pad128(int bytes) { return (bytes + 127) & ~127; }
 
 template <int MODE, bool FORCE>
 struct StageLayout {
   static constexpr int NRAW = MODE == MODE_ELASTIC ? 2 : (MODE == MODE_TANGENT ? 9 : 11);
-  static constexpr int NARR = 7 + NRAW + (FORCE ? 3 : 0);
+  // byte sizes of one box of each tensor, as a function of the box width
+  __host__ __device__ static constexpr int geom_b(int w) { return pad128(7 * w * 8); }
+  __host__ __device__ static constexpr int t0_b(int w) { return pad128((MODE == MODE_ELASTIC ? 1 : 9) * w * 8); }
+  __host__ __device__ static constexpr int t1_b(int w) { return (MODE == MODE_ELASTIC || MODE == MODE_TANGENT_REF) ? pad128(w * 8) : 0; }
+  __host__ __device__ static constexpr int t2_b(int w) { return MODE == MODE_TANGENT_REF ? pad128(w * 8) : 0; }
+  __host__ __device__ static constexpr int s_b(int w) { return FORCE ? pad128(3 * w * 8) : 0; }
+  __host__ __device__ static constexpr int box_b(int w) { return geom_b(w) + t0_b(w) + t1_b(w) + t2_b(w) + s_b(w); }
+  __host__ __device__ static constexpr int warp_b(int w) { return 2 * box_b(w) + 128; }  // + mbarrier
 };
 
+__device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(0), "r"(bar)
+               : "memory");
+}
+
 template <int MODE, bool FORCE, int MAXDEG>
-__global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A) {
+__global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
   constexpr int NP = 3;
   using L = StageLayout<MODE, FORCE>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (slice >= A.n_slices) return;  // warp-uniform; only warp-level synchronisation below
-  const int cap = A.stage_cap;
-  const size_t warp_bytes = (size_t)L::NARR * cap * sizeof(double) + 16;
-  double* buf = reinterpret_cast<double*>(smem_raw + warp * warp_bytes);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(buf + (size_t)L::NARR * cap);
-  const int32_t* runs = A.stage_runs + slice * (1 + 2 * FEM_STAGE_RMAX);
-  const int n_runs = runs[0];
-  int total = 0;
-  for (int r = 0; r < n_runs; ++r) total += runs[2 + 2 * r];
-  if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  if (lane == 0 && total > 0) {
-    const uint32_t bar = smem_u32(mbar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(L::NARR * total * 8)) : "memory");
-    int off = 0;
-    for (int r = 0; r < n_runs; ++r) {
-      const int start = runs[1 + 2 * r], len = runs[2 + 2 * r];
-#pragma unroll
-      for (int k = 0; k < L::NARR; ++k) {
-        const uint32_t dst = smem_u32(buf + (size_t)k * cap + off);
-        const double* src = A.stage_src[k] + start;
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(src), "r"((uint32_t)(len * 8)), "r"(bar)
-                     : "memory");
+  const int bw = A.boxw;
+  unsigned char* wbase = smem_raw + (size_t)warp * L::warp_b(bw);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * L::box_b(bw));
+  const int n_box = A.stage_box[slice * 3];
+  const bool staged = n_box >= 1 && n_box <= 2;  // warp-uniform
+  if (staged) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(mbar);
+      const uint32_t bytes_per_box = (uint32_t)((7 + L::NRAW + (FORCE ? 3 : 0)) * bw * 8);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_per_box * (uint32_t)n_box) : "memory");
+      for (int b = 0; b < n_box; ++b) {
+        const int start = A.stage_box[slice * 3 + 1 + b];
+        unsigned char* bb = wbase + (size_t)b * L::box_b(bw);
+        tma_box_2d(smem_u32(bb), &M.geom, start, bar);
+        bb += L::geom_b(bw);
+        tma_box_2d(smem_u32(bb), &M.t0, start, bar);
+        bb += L::t0_b(bw);
+        if (MODE == MODE_ELASTIC || MODE == MODE_TANGENT_REF) {
+          tma_box_2d(smem_u32(bb), &M.t1, start, bar);
+          bb += L::t1_b(bw);
+        }
+        if (MODE == MODE_TANGENT_REF) {
+          tma_box_2d(smem_u32(bb), &M.t2, start, bar);
+          bb += L::t2_b(bw);
+        }
+        if (FORCE) tma_box_2d(smem_u32(bb), &M.s, start, bar);
       }
-      off += len;
     }
   }
   // while the copies fly: node bookkeeping, incidence words, accumulator init
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A)
 #pragma unroll
   for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
   double f0 = 0.0, f1 = 0.0;
-  if (total > 0) {
+  if (staged) {
     const uint32_t bar = smem_u32(mbar);
     uint32_t ok = 0;
     do {
@@ -383,26 +412,47 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A)
 #pragma unroll
     for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
     if (!(word & 0x80000000u)) continue;
-    const int li = word & 0xFF;
-    const int la = (word >> 8) & 3;
+    const int la = (word >> 9) & 3;
     PointData<NP, MODE, FORCE> pd;
-    pd.w = buf[li];
+    if (staged) {
+      const int li = word & 0x1FF;
+      const int b = li >= bw ? 1 : 0;
+      const int o = li - b * bw;
+      const unsigned char* bb = wbase + (size_t)b * L::box_b(bw);
+      const double* g = reinterpret_cast<const double*>(bb) + o;
+      pd.w = g[0];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      pd.d1[p] = buf[(size_t)(1 + p) * cap + li];
-      pd.d2[p] = buf[(size_t)(4 + p) * cap + li];
-    }
+      for (int p = 0; p < NP; ++p) {
+        pd.d1[p] = g[(1 + p) * bw];
+        pd.d2[p] = g[(4 + p) * bw];
+      }
+      bb += L::geom_b(bw);
+      const double* t0 = reinterpret_cast<const double*>(bb) + o;
+      if (MODE == MODE_ELASTIC) {
+        pd.raw[0] = t0[0];
+        pd.raw[1] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+      } else {
 #pragma unroll
-    for (int k = 0; k < L::NRAW; ++k) pd.raw[k] = buf[(size_t)(7 + k) * cap + li];
-    if (FORCE) {
+        for (int k = 0; k < 9; ++k) pd.raw[k] = t0[k * bw];
+        if (MODE == MODE_TANGENT_REF) {
+          pd.raw[MODE == MODE_TANGENT_REF ? 9 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+          pd.raw[MODE == MODE_TANGENT_REF ? 10 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw)) + o)[0];
+        }
+      }
+      if (FORCE) {
+        const double* sp = reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw) + L::t2_b(bw)) + o;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) pd.s[k] = buf[(size_t)(7 + L::NRAW + k) * cap + li];
+        for (int k = 0; k < 3; ++k) pd.s[k] = sp[k * bw];
+      }
+    } else {  // direct loads (slices with more than two boxes)
+      const uint32_t key = A.inc_key[sbase + (int64_t)i * 32 + lane];
+      load_point<NP, MODE, FORCE>(A, (int64_t)(key >> 3), pd);
     }
     double tx[3], ty[3];
     point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
 #pragma unroll
     for (int lb = 0; lb < NP; ++lb) {
-      const int slot = (word >> (10 + 4 * lb)) & 15;
+      const int slot = (word >> (11 + 4 * lb)) & 15;
       const double b1 = pd.d1[lb], b2 = pd.d2[lb];
       const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
       const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
@@ -440,36 +490,271 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A)
     }
 }
 
+// ---- variant D: persistent, software-pipelined TMA staging ------------------------------------------------------
+// Same staging and arithmetic as variant C, but each warp walks many slices and keeps the TMA engine one half-slice
+// ahead: box 0 of slice s+1 is requested as soon as the incidences living in box 0 of slice s are consumed, box 1 of
+// s+1 after box 1 of s.  The dependent chain (box table -> TMA -> compute -> store) of a slice is thereby overlapped
+// with the computation of the previous one without any extra shared memory.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+template <int MODE, bool FORCE>
+__device__ __forceinline__ void issue_box(const StageMaps& M, unsigned char* bb, int bw, int start, uint32_t bar) {
+  using L = StageLayout<MODE, FORCE>;
+  const uint32_t bytes = (uint32_t)((7 + L::NRAW + (FORCE ? 3 : 0)) * bw * 8);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  tma_box_2d(smem_u32(bb), &M.geom, start, bar);
+  bb += L::geom_b(bw);
+  tma_box_2d(smem_u32(bb), &M.t0, start, bar);
+  bb += L::t0_b(bw);
+  if (MODE == MODE_ELASTIC || MODE == MODE_TANGENT_REF) {
+    tma_box_2d(smem_u32(bb), &M.t1, start, bar);
+    bb += L::t1_b(bw);
+  }
+  if (MODE == MODE_TANGENT_REF) {
+    tma_box_2d(smem_u32(bb), &M.t2, start, bar);
+    bb += L::t2_b(bw);
+  }
+  if (FORCE) tma_box_2d(smem_u32(bb), &M.s, start, bar);
+}
+
+template <int MODE, bool FORCE, int MAXDEG>
+__global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
+  constexpr int NP = 3;
+  using L = StageLayout<MODE, FORCE>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bw = A.boxw;
+  unsigned char* wbase = smem_raw + (size_t)warp * L::warp_b(bw);
+  unsigned char* box0 = wbase;
+  unsigned char* box1 = wbase + L::box_b(bw);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * L::box_b(bw));  // [0] box 0, [1] box 1
+  const uint32_t bar0 = smem_u32(mbar), bar1 = smem_u32(mbar + 1);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar1), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_slices = A.n_slices;
+  int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  uint32_t ph0 = 0, ph1 = 0;
+  constexpr int CH = 8;  // plan guarantees <= 8 incidences per node when stage_ok
+  // Per-slice bookkeeping, fetched one slice ahead (two for the SELL offsets the incidence words depend on):
+  //   box table {nb, st0, st1}, node degree/base, SELL offset + width, incidence words.
+  struct Book { int nb, st0, st1, deg, width; int64_t base, sbase; };
+  auto load_box = [&](int64_t s, Book& k) {
+    k.nb = 0; k.st0 = 0; k.st1 = 0;
+    if (s < n_slices) { k.nb = A.stage_box[s * 3]; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2]; }
+  };
+  auto load_node = [&](int64_t s, Book& k) {
+    k.deg = 0; k.base = 0;
+    const int64_t a = s * 32 + lane;
+    if (s < n_slices && a < A.n_n) {
+      const int nbp = A.nbr_ptr[a];
+      k.deg = A.nbr_ptr[a + 1] - nbp;
+      k.base = 4 * (int64_t)nbp;
+    }
+  };
+  auto load_sell = [&](int64_t s, Book& k) {
+    k.sbase = 0; k.width = 0;
+    if (s < n_slices) { k.sbase = A.slice_ptr[s]; k.width = (int)((A.slice_ptr[s + 1] - k.sbase) >> 5); }
+  };
+  Book cur, nxt;
+  uint32_t words[CH], nwords[CH];
+  load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
+  load_sell(slice + n_warps, nxt);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
+  if (slice < n_slices && lane == 0 && cur.nb >= 1 && cur.nb <= 2) {
+    issue_box<MODE, FORCE>(M, box0, bw, cur.st0, bar0);
+    if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
+  }
+  while (slice < n_slices) {
+    const int64_t next = slice + n_warps;
+    // requests for the next slice (and the SELL offsets of the one after) fly during this slice's computation
+    load_box(next, nxt);
+    load_node(next, nxt);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) nwords[i] = (i < nxt.width) ? __ldcs(A.inc_stage + nxt.sbase + (int64_t)i * 32 + lane) : 0u;
+    Book nn;
+    load_sell(next + n_warps, nn);
+    const int nb = cur.nb;
+    const bool staged = nb >= 1 && nb <= 2;
+    const int64_t a = slice * 32 + lane;
+    double acc[MAXDEG][4];
+#pragma unroll
+    for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    double f0 = 0.0, f1 = 0.0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      // pass 0: incidences whose element lives in box 0 (or every incidence on the direct-load path); pass 1: box 1.
+      // A node's incidences are ascending in element id and box 0 precedes box 1, so the accumulation order is kept.
+      if (staged) {
+        if (pass == 0) { mbar_wait(bar0, ph0); ph0 ^= 1; }
+        else if (nb == 2) { mbar_wait(bar1, ph1); ph1 ^= 1; }
+      }
+      if (pass == 0 || (staged && nb == 2)) {
+#pragma unroll 1
+        for (int i = 0; i < CH; ++i) {  // rotate the whole queue so that it is back in place for the next pass
+          const uint32_t word = words[0];
+#pragma unroll
+          for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
+          words[CH - 1] = word;
+          if (!(word & 0x80000000u)) continue;
+          const int li = word & 0x1FF;
+          if (staged && ((li >= bw) != (pass == 1))) continue;
+          const int la = (word >> 9) & 3;
+          PointData<NP, MODE, FORCE> pd;
+          if (staged) {
+            const int o = li - pass * bw;
+            const unsigned char* bb = pass ? box1 : box0;
+            const double* g = reinterpret_cast<const double*>(bb) + o;
+            pd.w = g[0];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              pd.d1[p] = g[(1 + p) * bw];
+              pd.d2[p] = g[(4 + p) * bw];
+            }
+            bb += L::geom_b(bw);
+            const double* t0 = reinterpret_cast<const double*>(bb) + o;
+            if (MODE == MODE_ELASTIC) {
+              pd.raw[0] = t0[0];
+              pd.raw[1] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+            } else {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) pd.raw[k] = t0[k * bw];
+              if (MODE == MODE_TANGENT_REF) {
+                pd.raw[MODE == MODE_TANGENT_REF ? 9 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+                pd.raw[MODE == MODE_TANGENT_REF ? 10 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw)) + o)[0];
+              }
+            }
+            if (FORCE) {
+              const double* sp = reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw) + L::t2_b(bw)) + o;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) pd.s[k] = sp[k * bw];
+            }
+          } else {  // direct loads (slices with more than two boxes); i-th entry of the queue is incidence i
+            const uint32_t key = A.inc_key[cur.sbase + (int64_t)i * 32 + lane];
+            load_point<NP, MODE, FORCE>(A, (int64_t)(key >> 3), pd);
+          }
+          double tx[3], ty[3];
+          point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
+#pragma unroll
+          for (int lb = 0; lb < NP; ++lb) {
+            const int slot = (word >> (11 + 4 * lb)) & 15;
+            const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+            const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
+            const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
+#define FEM_UPD(J)                               \
+  case J:                                        \
+    if (J < MAXDEG) {                            \
+      acc[J < MAXDEG ? J : 0][0] = (acc[J < MAXDEG ? J : 0][0] + p00) + p01; \
+      acc[J < MAXDEG ? J : 0][1] = (acc[J < MAXDEG ? J : 0][1] + p10) + p11; \
+      acc[J < MAXDEG ? J : 0][2] = (acc[J < MAXDEG ? J : 0][2] + p20) + p21; \
+      acc[J < MAXDEG ? J : 0][3] = (acc[J < MAXDEG ? J : 0][3] + p30) + p31; \
+    }                                            \
+    break;
+            switch (slot) {
+              FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
+              default: break;
+            }
+#undef FEM_UPD
+          }
+        }
+      }
+      __syncwarp();  // every lane is done reading this pass's box: it may be overwritten by the next slice's copy
+      if (lane == 0 && nxt.nb >= 1 && nxt.nb <= 2) {
+        if (pass == 0) issue_box<MODE, FORCE>(M, box0, bw, nxt.st0, bar0);
+        else if (nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
+      }
+    }
+    if (a < A.n_n) {
+      const int deg = cur.deg;
+      if (FORCE) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+      double2* row0 = reinterpret_cast<double2*>(A.K_vals + cur.base);
+      double2* row1 = row0 + deg;
+#pragma unroll
+      for (int j = 0; j < MAXDEG; ++j)
+        if (j < deg) {
+          double2 v0 = make_double2(acc[j][0], acc[j][1]), v1 = make_double2(acc[j][2], acc[j][3]);
+          if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction
+            const double2 k0 = reinterpret_cast<const double2*>(A.Kel + cur.base)[j];
+            const double2 k1 = reinterpret_cast<const double2*>(A.Kel + cur.base)[deg + j];
+            v0.x = k0.x + v0.x; v0.y = k0.y + v0.y; v1.x = k1.x + v1.x; v1.y = k1.y + v1.y;
+          }
+          __stcs(row0 + j, v0);
+          __stcs(row1 + j, v1);
+        }
+    }
+    slice = next;
+    cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
+    cur.sbase = nxt.sbase; cur.width = nxt.width;
+    nxt.sbase = nn.sbase; nxt.width = nn.width;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) words[i] = nwords[i];
+  }
+}
+
 template <int MODE, bool FORCE>
 static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   using L = StageLayout<MODE, FORCE>;
-  A.stage_runs = P->stage_runs;
+  const int bw = P->stage_boxw;
+  A.stage_box = P->stage_box;
   A.inc_stage = P->inc_stage;
-  A.stage_cap = P->stage_cap;
-  int k = 0;
-  A.stage_src[k++] = P->weight;
-  for (int p = 0; p < 3; ++p) A.stage_src[k++] = P->dphi1 + (int64_t)p * P->n_int;
-  for (int p = 0; p < 3; ++p) A.stage_src[k++] = P->dphi2 + (int64_t)p * P->n_int;
+  A.boxw = bw;
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  if ((A.DS && mis(A.DS)) || (A.shear && mis(A.shear)) || (A.bulk && mis(A.bulk)) || (FORCE && mis(A.S))) return -1;  // TMA needs 16-byte aligned rows
+  StageMaps M;
+  memset(&M, 0, sizeof(M));
+  M.geom = P->geom_map;
+  int rc = FEM_OK;
   if (MODE == MODE_ELASTIC) {
-    A.stage_src[k++] = A.shear;
-    A.stage_src[k++] = A.bulk;
+    if ((rc = fem_encode_rows_map(&M.t0, A.shear, P->n_int, 1, bw)) != FEM_OK) return rc;
+    if ((rc = fem_encode_rows_map(&M.t1, A.bulk, P->n_int, 1, bw)) != FEM_OK) return rc;
   } else {
-    for (int q = 0; q < 9; ++q) A.stage_src[k++] = A.DS + (int64_t)q * P->n_int;
+    if ((rc = fem_encode_rows_map(&M.t0, A.DS, P->n_int, 9, bw)) != FEM_OK) return rc;
     if (MODE == MODE_TANGENT_REF) {
-      A.stage_src[k++] = A.shear;
-      A.stage_src[k++] = A.bulk;
+      if ((rc = fem_encode_rows_map(&M.t1, A.shear, P->n_int, 1, bw)) != FEM_OK) return rc;
+      if ((rc = fem_encode_rows_map(&M.t2, A.bulk, P->n_int, 1, bw)) != FEM_OK) return rc;
     }
   }
-  if (FORCE)
-    for (int q = 0; q < 3; ++q) A.stage_src[k++] = A.S + (int64_t)q * P->n_int;
-  for (int i = 0; i < k; ++i)
-    if (reinterpret_cast<uintptr_t>(A.stage_src[i]) & 15u) return -1;  // bulk copies need 16-byte aligned rows: fall back
-  const int warps = 4;
-  const size_t smem = warps * ((size_t)L::NARR * P->stage_cap * sizeof(double) + 16);
+  if (FORCE && (rc = fem_encode_rows_map(&M.s, A.S, P->n_int, 3, bw)) != FEM_OK) return rc;
+  int warps = 4;
+  size_t smem = (size_t)warps * L::warp_b(bw);
   if (smem > 227 * 1024) return -1;
-  auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
-  FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A);
+  if (g_fem_tuning.assemble_variant == 7) {  // one slice per warp, no pipelining
+    auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A, M);
+  } else {                                   // persistent, software-pipelined
+    auto kern = assemble_rows_tmap_kernel<MODE, FORCE, 8>;
+    // warps per CTA (4..6) that packs the most warps into the 227 KB of an SM (1 KB per CTA is reserved)
+    int best = 0;
+    for (int w = 4; w <= 6; ++w) {
+      const size_t sm = (size_t)w * L::warp_b(bw);
+      const int per = (int)((227 * 1024) / (sm + 1024));
+      if (per * w > best) { best = per * w; warps = w; }
+    }
+    if (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= 6) warps = g_fem_tuning.assemble_warps;
+    smem = (size_t)warps * L::warp_b(bw);
+    FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    FEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return -1;
+    int64_t blocks = (int64_t)per_sm * P->sm_count;
+    const int64_t need = fem_div_up(P->n_slices, warps);
+    if (blocks > need) blocks = need;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(A, M);
+  }
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -513,7 +798,7 @@ template <int MODE, bool FORCE>
 static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   // variant B (register accumulators) for P1/Q1 meshes of bounded valence; variant A (shared memory) otherwise
   const int variant = g_fem_tuning.assemble_variant;
-  if (MODE != MODE_FORCE_ONLY && P->stage_ok && (variant == 0 || variant == 6)) {
+  if (MODE != MODE_FORCE_ONLY && P->stage_ok && (variant == 0 || variant == 6 || variant == 7)) {
     const int rc = launch_assemble_tma<MODE == MODE_FORCE_ONLY ? MODE_TANGENT : MODE, FORCE>(P, A, st);
     if (rc >= 0) return rc;  // -1: inputs not 16-byte aligned / too much shared memory -> register kernel
   }

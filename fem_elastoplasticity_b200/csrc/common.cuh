@@ -2,6 +2,7 @@
 // strain and force kernels reproduce scipy's accumulation order bit-for-bit, so the compiler
 // must not contract a*b+c.  Kernels that do not need that (SpMV, PCG) call fma() explicitly.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -13,8 +14,9 @@
 #define FEM_MAX_NQ 9
 #define FEM_WARP 32
 #define FEM_INVALID_KEY 0xFFFFFFFFu
-#define FEM_STAGE_RMAX 4
-#define FEM_STAGE_CAP 192   // max staged elements per slice (li must fit 8 bits)
+#define FEM_STAGE_MAXBOXW 96   // widest TMA box (elements); longer runs are split
+// 2-D tensor map over `rows` SoA rows of n_int doubles (row stride n_int), box = rows x boxw
+int fem_encode_rows_map(CUtensorMap* out, const double* base, int64_t n_int, int rows, int boxw);
 
 void fem_set_error(const char* fmt, ...);
 
@@ -79,9 +81,12 @@ struct fem_plan {
   double* dscratch;  // small device scratch (8 doubles)
   // TMA staging data of the P1 assembly kernel (valid when stage_ok): per 32-node slice the touched elements as
   // <= FEM_STAGE_RMAX runs of consecutive ids (16-byte aligned), and per incidence its position in the staged buffer
-  int stage_ok, stage_cap;
-  int32_t* stage_runs;   // [n_slices][1 + 2*FEM_STAGE_RMAX]: count, then (start, length) pairs
-  uint32_t* inc_stage;   // [sell_entries]: li | la<<8 | slot0<<10 | slot1<<14 | slot2<<18 | valid<<31
+  int stage_ok, stage_boxw;
+  int64_t stage_fallback_slices;
+  int32_t* stage_box;    // [n_slices][3]: number of boxes, start element of box 0, of box 1 (TMA path when <= 2 boxes)
+  uint32_t* inc_stage;   // [sell_entries]: li | la<<9 | slot0<<11 | slot1<<15 | slot2<<19 | valid<<31, li = box*boxw + offset
+  double* geom;          // one allocation [1 + 2*n_p][n_int]: weight, dphi1 rows, dphi2 rows (one TMA box brings all rows)
+  CUtensorMap geom_map;
   int64_t bytes;
 };
 

@@ -342,22 +342,26 @@ __global__ void __launch_bounds__(256) geometry_kernel(int64_t n_e, int64_t n_n,
 
 
 // ------------------------------------------------------------------------------------------------
-// Staging plan for the TMA assembly kernel (P1, node degree <= 8): the set of elements touched by the 32 nodes of a
-// slice, expressed as a few runs of consecutive element ids, so that each SoA array can be brought into shared
-// memory with one bulk copy per run.  Every lane of the warp builds the same run list redundantly (no divergence).
+// Staging plan for the TMA assembly kernel (P1, node degree <= 8).  The elements touched by the 32 nodes of a slice
+// form a few runs of consecutive ids; each run is covered by fixed-width boxes so that one 2-D TMA box copy brings
+// all SoA rows of a tensor (7 geometry rows, 9 DS rows, 3 S rows) for a run.  Pass A (boxw == 0) measures the longest
+// run; pass B assigns boxes and the per-incidence position li = box*boxw + offset.  Slices needing more than two
+// boxes (row ends of a structured mesh, irregular meshes) are processed by the kernel's direct-load path.
+// Every lane of the warp builds the same run list redundantly (no divergence).
 // ------------------------------------------------------------------------------------------------
-__global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, const int64_t* __restrict__ slice_ptr,
+__global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int boxw, const int64_t* __restrict__ slice_ptr,
                             const uint32_t* __restrict__ inc_key, const uint32_t* __restrict__ inc_meta,
-                            int32_t* __restrict__ stage_runs, uint32_t* __restrict__ inc_stage, int* fail, int* cap_max) {
+                            int32_t* __restrict__ stage_box, uint32_t* __restrict__ inc_stage, int* flags) {
+  // flags: [0] slices that cannot be described (too many incidences/runs), [1] longest run, [2] slices with > 2 boxes
   constexpr int RT = 8, W = 8;
   const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slice >= n_slices) return;
   const int64_t sbase = slice_ptr[slice];
   const int width = (int)((slice_ptr[slice + 1] - sbase) >> 5);
-  int32_t* out = stage_runs + slice * (1 + 2 * FEM_STAGE_RMAX);
+  int32_t* out = stage_box + slice * 3;
   if (width > W) {
-    if (lane == 0) { atomicAdd(fail, 1); out[0] = 0; }
+    if (lane == 0) { atomicAdd(flags, 1); out[0] = 99; }
     return;
   }
   uint32_t keys[W];
@@ -398,17 +402,24 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, const 
     else { rs[m] = rs[r]; re[m] = re[r]; ++m; }
   }
   nr = m;
-  int total = 0;
-  for (int r = 0; r < nr; ++r) total += re[r] - rs[r];
-  if (nr > FEM_STAGE_RMAX || total > FEM_STAGE_CAP) bad = true;
   if (bad) {
-    if (lane == 0) { atomicAdd(fail, 1); out[0] = 0; }
+    if (lane == 0) { atomicAdd(flags, 1); out[0] = 99; }
     return;
   }
+  if (boxw == 0) {  // pass A: longest run
+    int longest = 0;
+    for (int r = 0; r < nr; ++r) longest = max(longest, re[r] - rs[r]);
+    if (lane == 0) atomicMax(flags + 1, longest);
+    return;
+  }
+  int nb = 0;
+  for (int r = 0; r < nr; ++r) nb += (re[r] - rs[r] + boxw - 1) / boxw;
   if (lane == 0) {
-    out[0] = nr;
-    for (int r = 0; r < nr; ++r) { out[1 + 2 * r] = rs[r]; out[2 + 2 * r] = re[r] - rs[r]; }
-    atomicMax(cap_max, total);
+    out[0] = nb;
+    if (nb > 2) atomicAdd(flags + 2, 1);
+    int b = 0;
+    for (int r = 0; r < nr && b < 2; ++r)
+      for (int st = rs[r]; st < re[r] && b < 2; st += boxw) out[1 + b++] = st;
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
@@ -417,17 +428,47 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, const 
     uint32_t word = 0;
     if (keys[i] != FEM_INVALID_KEY) {
       const int x = (int)(keys[i] >> 3);
-      int off = 0, li = 0;
+      int b0 = 0, li = 0;
       for (int r = 0; r < nr; ++r) {
-        if (x >= rs[r] && x < re[r]) li = off + x - rs[r];
-        off += re[r] - rs[r];
+        if (x >= rs[r] && x < re[r]) li = (b0 + (x - rs[r]) / boxw) * boxw + (x - rs[r]) % boxw;
+        b0 += (re[r] - rs[r] + boxw - 1) / boxw;
       }
+      if (nb > 2) li = 0;
       const uint32_t meta = inc_meta[at];  // la | pos0<<8 | pos1<<16 | pos2<<24
-      word = (uint32_t)li | ((meta & 3u) << 8) | (((meta >> 8) & 15u) << 10) | (((meta >> 16) & 15u) << 14) |
-             (((meta >> 24) & 15u) << 18) | 0x80000000u;
+      word = (uint32_t)li | ((meta & 3u) << 9) | (((meta >> 8) & 15u) << 11) | (((meta >> 16) & 15u) << 15) |
+             (((meta >> 24) & 15u) << 19) | 0x80000000u;
     }
     inc_stage[at] = word;
   }
+}
+
+typedef CUresult (*fem_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int fem_encode_rows_map(CUtensorMap* out, const double* base, int64_t n_int, int rows, int boxw) {
+  static fem_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      fem_set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return FEM_ERR_CUDA;
+    }
+    fn = (fem_encode_tiled_fn)p;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)n_int, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)n_int * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fem_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d boxw=%d)", (int)r, rows, boxw);
+    return FEM_ERR_CUDA;
+  }
+  return FEM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -542,27 +583,43 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     fill_sell<<<grid(n_n), threads, 0, st>>>(n_n, n_e, n_p, P->meta_words, P->sell_entries, P->elem, inc_ptr, keys, P->nbr_ptr,
                                              P->nbr_idx, P->slice_ptr, P->inc_key, P->inc_meta);
     // geometry
-    if ((rc = dmalloc(P, &P->dphi1, (int64_t)n_p * P->n_int)) != FEM_OK) break;
-    if ((rc = dmalloc(P, &P->dphi2, (int64_t)n_p * P->n_int)) != FEM_OK) break;
-    if ((rc = dmalloc(P, &P->weight, P->n_int)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->geom, (int64_t)(1 + 2 * n_p) * P->n_int)) != FEM_OK) break;
+    P->weight = P->geom;
+    P->dphi1 = P->geom + P->n_int;
+    P->dphi2 = P->geom + (int64_t)(1 + n_p) * P->n_int;
     if ((rc = dmalloc(P, &P->dscratch, 16)) != FEM_OK) break;
     if ((rc = launch_geometry(P, coord, flags + 3, st)) != FEM_OK) break;
     // TMA staging plan (P1 meshes of bounded valence whose slices touch few runs of consecutive elements)
     P->stage_ok = 0;
-    if (n_p == 3 && P->n_q == 1 && P->max_degree <= 8 && P->max_inc <= 8 && (P->n_int % 2) == 0) {
-      int* sflags = nullptr;  // [0] failed slices, [1] max staged elements
-      if (cudaMalloc(&sflags, 2 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc sflags"); break; }
-      cudaMemsetAsync(sflags, 0, 2 * sizeof(int), st);
-      if ((rc = dmalloc(P, &P->stage_runs, P->n_slices * (1 + 2 * FEM_STAGE_RMAX))) != FEM_OK) break;
+    if (n_p == 3 && P->n_q == 1 && P->max_degree <= 8 && P->max_inc <= 8 && (P->n_int % 2) == 0 && P->n_int >= 64) {
+      int* sflags = nullptr;
+      if (cudaMalloc(&sflags, 3 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc sflags"); break; }
+      cudaMemsetAsync(sflags, 0, 3 * sizeof(int), st);
+      if ((rc = dmalloc(P, &P->stage_box, P->n_slices * 3)) != FEM_OK) break;
       if ((rc = dmalloc(P, &P->inc_stage, P->sell_entries)) != FEM_OK) break;
-      build_stage<<<(unsigned)((P->n_slices * 32 + threads - 1) / threads), threads, 0, st>>>(
-          n_n, P->n_slices, P->n_int, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_runs, P->inc_stage, sflags, sflags + 1);
-      int hs[2] = {1, 0};
+      const unsigned sblocks = (unsigned)((P->n_slices * 32 + threads - 1) / threads);
+      build_stage<<<sblocks, threads, 0, st>>>(n_n, P->n_slices, P->n_int, 0, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_box,
+                                               P->inc_stage, sflags);
+      int hs[3] = {1, 0, 0};
       cudaStreamSynchronize(st);
       cudaMemcpy(hs, sflags, sizeof(hs), cudaMemcpyDeviceToHost);
+      if (hs[0] == 0 && hs[1] > 0) {
+        int boxw = (hs[1] + 1) & ~1;
+        if (boxw > FEM_STAGE_MAXBOXW) boxw = FEM_STAGE_MAXBOXW;
+        if (boxw < 16) boxw = 16;
+        cudaMemsetAsync(sflags, 0, 3 * sizeof(int), st);
+        build_stage<<<sblocks, threads, 0, st>>>(n_n, P->n_slices, P->n_int, boxw, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_box,
+                                                 P->inc_stage, sflags);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hs, sflags, sizeof(hs), cudaMemcpyDeviceToHost);
+        P->stage_boxw = boxw;
+        P->stage_fallback_slices = hs[2];
+        // worth it only when most slices take the TMA path
+        if (hs[0] == 0 && (int64_t)hs[2] * 8 <= P->n_slices &&
+            fem_encode_rows_map(&P->geom_map, P->geom, P->n_int, 7, boxw) == FEM_OK)
+          P->stage_ok = 1;
+      }
       cudaFree(sflags);
-      P->stage_ok = (hs[0] == 0 && hs[1] > 0);
-      P->stage_cap = (hs[1] + 1) & ~1;
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fem_set_error("plan build failed: %s", cudaGetErrorString(e)); rc = FEM_ERR_CUDA; break; }
@@ -623,10 +680,10 @@ extern "C" int fem_plan_create(int64_t n_n, int64_t n_e, int n_p, int n_q, const
 
 extern "C" int fem_plan_destroy(fem_plan* P) {
   if (!P) return FEM_OK;
-  cudaFree(P->stage_runs); cudaFree(P->inc_stage);
+  cudaFree(P->stage_box); cudaFree(P->inc_stage);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
-  cudaFree(P->dphi1); cudaFree(P->dphi2); cudaFree(P->weight); cudaFree(P->dscratch);
+  cudaFree(P->geom); cudaFree(P->dscratch);
   delete P;
   return FEM_OK;
 }
@@ -666,7 +723,7 @@ extern "C" int fem_plan_geometry(const fem_plan* P, const double** dphi1, const 
 extern "C" int fem_plan_stage_info(const fem_plan* P, int* stage_ok, int* stage_cap) {
   FEM_REQUIRE(P, "plan");
   if (stage_ok) *stage_ok = P->stage_ok;
-  if (stage_cap) *stage_cap = P->stage_cap;
+  if (stage_cap) *stage_cap = P->stage_boxw;
   return FEM_OK;
 }
 extern "C" int64_t fem_plan_bytes(const fem_plan* P) { return P ? P->bytes : 0; }

@@ -95,7 +95,7 @@ class FemPlan:
         self.bytes = int(_lib.load().fem_plan_bytes(self._h))
 
     def stage_info(self):
-        """(stage_ok, staged elements per slice) of the TMA-staged assembly kernel."""
+        """(stage_ok, TMA box width in elements) of the TMA-staged assembly kernel."""
         ok, cap = C.c_int(), C.c_int()
         call("fem_plan_stage_info", self._h, C.byref(ok), C.byref(cap))
         return int(ok.value), int(cap.value)

@@ -69,8 +69,8 @@ int fem_plan_blocks(const fem_plan* plan, const int32_t** nbr_ptr, const int32_t
 /* dphi1, dphi2 (n_p, n_int) and weight (n_int,) = |det J| * wf  (:545-546, :585); owned by the plan.
  * These are exactly the stored values of the reference's sparse B (:549-571).                    */
 int fem_plan_geometry(const fem_plan* plan, const double** dphi1, const double** dphi2, const double** weight);
-/* whether the TMA-staged assembly kernel applies to this mesh (P1, degree <= 8, slices touching <= 4 runs of
- * consecutive elements) and the staged elements per slice */
+/* whether the TMA-staged assembly kernel applies to this mesh (P1, degree <= 8, most 32-node slices touching at most two
+ * runs of consecutive elements) and the width (elements) of its TMA boxes */
 int fem_plan_stage_info(const fem_plan* plan, int* stage_ok, int* stage_cap);
 /* bytes of device memory held by the plan */
 int64_t fem_plan_bytes(const fem_plan* plan);
