@@ -52,7 +52,7 @@ def main():
     r = dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm)
     kel_ref = None
     k, F = P.empty(P.nnz), P.empty(P.n_dof)
-    for v, name in ((2, "reg"), (7, "tma"), (6, "tmapipe")):
+    for v, name in ((2, "reg"), (7, "tma"), (6, "tmapipe"), (0, "default")):
         knob("assemble_variant", v)
         res[f"assemble_elastic_{name}_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
         kel = k.clone()
