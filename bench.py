@@ -246,6 +246,19 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t0.elapsed_time(t1)
     per = {p: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in rec])) for i, p in enumerate(phases)}
+    # ---- isolated kernels (same inputs, outside the step): K_tangent alone and K_elast
+    def iso(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        b0, b1 = ev(), ev()
+        b0.record()
+        for _ in range(reps):
+            fn()
+        b1.record()
+        torch.cuda.synchronize()
+        return b0.elapsed_time(b1) / reps
+    t_tan_only = iso(lambda: P.assemble_tangent(rm["ds"], out=k_tan))
+    t_el_only = iso(lambda: P.assemble_elastic(G, Kb, out=k_tan))
     # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     ds_host = torch.empty((9, P.n_int), dtype=torch.float64, pin_memory=True)
     ds_host.copy_(rm["ds"])
@@ -267,11 +280,11 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = a0.elapsed_time(a1) / e2e_steps
     # ---- reduce over ranks (max time)
-    vec = torch.tensor([total_ms, per["strain"], per["return_map"], per["assembly"], per["pcg"], per["criterion"], e2e_ms],
-                       dtype=torch.float64, device=dev)
+    vec = torch.tensor([total_ms, per["strain"], per["return_map"], per["assembly"], per["pcg"], per["criterion"], e2e_ms,
+                        t_tan_only, t_el_only], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-    total_ms, t_strain, t_rm, t_asm, t_pcg, t_crit, e2e_ms = [float(v) for v in vec.cpu()]
+    total_ms, t_strain, t_rm, t_asm, t_pcg, t_crit, e2e_ms, t_tan_only, t_el_only = [float(v) for v in vec.cpu()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -283,6 +296,7 @@ def run_gpu(args):
     ms_step = total_ms / args.steps
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9  # noqa: E731
     algo = {
+        "tangent_only": 212.0 * P.n_e, "elastic": 156.0 * P.n_e,
         "assembly": 212.0 * P.n_e + 24.0 * P.n_int + 8.0 * P.n_dof,
         "return_map": 193.0 * P.n_int,
         "strain": 12.0 * P.n_e + 8.0 * P.n_dof + 24.0 * P.n_int,
@@ -296,12 +310,14 @@ def run_gpu(args):
             traffic = json.load(f).get("assemble_rows_kernel")
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "assemble_rows_kernel<3,1,TANGENT,FORCE> (K_tangent + F, one pass)",
+    roof = {"bound": "hbm", "kernel": "assemble_rows_tmap_kernel<TANGENT,FORCE> (K_tangent + internal force, one pass, TMA-staged)",
             "achieved": gbs(algo["assembly"], t_asm), "peak": peak, "unit": "GB/s", "frac": gbs(algo["assembly"], t_asm) / peak,
             "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["assembly"],
             "frac_of_8TBs_nominal": gbs(algo["assembly"], t_asm) / 8000.0}
     rooflines = {k: {"achieved": gbs(algo[a], ms), "frac": gbs(algo[a], ms) / peak, "ms": ms, "algorithmic_bytes": algo[a]}
                  for k, a, ms in (("dp_return_map", "return_map", t_rm), ("strain", "strain", t_strain),
+                                  ("assemble_tangent_only(isolated)", "tangent_only", t_tan_only),
+                                  ("assemble_elastic(isolated)", "elastic", t_el_only),
                                   ("pcg_iteration(spmv+2 vector kernels)", "pcg_iter", pcg_ms_iter),
                                   ("criterion(3 spmv)", "spmv", t_crit / 3.0))}
     line = {
@@ -316,7 +332,9 @@ def run_gpu(args):
                    "plan_build_s": t_plan, "plan_bytes": P.bytes},
         "parts": {"tangent_assembly_melem_s": n_e_tot / (t_asm * 1e-3) / 1e6, "return_map_mpts_s": n_int_tot / (t_rm * 1e-3) / 1e6,
                   "pcg_newton_s_per_step": ms_step * 1e-3, "pcg_ms_per_iter": pcg_ms_iter, "strain_ms": t_strain, "criterion_ms": t_crit,
-                  "assembly_ms": t_asm, "return_map_ms": t_rm, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
+                  "assembly_ms": t_asm, "return_map_ms": t_rm, "tangent_only_isolated_ms": t_tan_only,
+                  "tangent_only_isolated_melem_s": n_e_tot / (t_tan_only * 1e-3) / 1e6,
+                  "elastic_isolated_melem_s": n_e_tot / (t_el_only * 1e-3) / 1e6, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
         "roofline": roof, "rooflines": rooflines, "clocks": clocks,
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent on pinned host DS -> host K values"},

@@ -30,6 +30,7 @@ struct AsmArgs {
   const int32_t* stage_box;
   const uint32_t* inc_stage;
   int boxw;
+  unsigned long long* slice_counter;  // dynamic tile scheduler of the persistent kernels (zeroed before launch)
   int acc_rows;         // 4 * max_degree
   double dev2[9];       // 2*Dev (column-major) formed as numpy forms it (:579-582)
   double vol[9];
@@ -543,9 +544,18 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t n_slices = A.n_slices;
-  int64_t slice = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  // Dynamic tile scheduler: slices are claimed in ascending order from a global counter, so the set of slices in flight
+  // is a window that slides smoothly through the mesh.  (A static warp + k*n_warps assignment advances in lock-step
+  // rounds: the two node rows that share a row of elements then fetch it at the same instant and both miss in L2 -
+  // measured 1.5x DRAM reads.)  The claim for slice s+2 is made while slice s is being computed.
+  auto claim = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(A.slice_counter, 1ULL);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t slice = claim();
+  int64_t slice1 = claim();  // the slice after the current one
   uint32_t ph0 = 0, ph1 = 0;
   constexpr int CH = 8;  // plan guarantees <= 8 incidences per node when stage_ok
   // Per-slice bookkeeping, fetched one slice ahead (two for the SELL offsets the incidence words depend on):
@@ -571,7 +581,7 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
   Book cur, nxt;
   uint32_t words[CH], nwords[CH];
   load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
-  load_sell(slice + n_warps, nxt);
+  load_sell(slice1, nxt);
 #pragma unroll
   for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
   if (slice < n_slices && lane == 0 && cur.nb >= 1 && cur.nb <= 2) {
@@ -579,14 +589,15 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
     if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
   }
   while (slice < n_slices) {
-    const int64_t next = slice + n_warps;
+    const int64_t next = slice1;
+    const int64_t slice2 = claim();
     // requests for the next slice (and the SELL offsets of the one after) fly during this slice's computation
     load_box(next, nxt);
     load_node(next, nxt);
 #pragma unroll
     for (int i = 0; i < CH; ++i) nwords[i] = (i < nxt.width) ? __ldcs(A.inc_stage + nxt.sbase + (int64_t)i * 32 + lane) : 0u;
     Book nn;
-    load_sell(next + n_warps, nn);
+    load_sell(slice2, nn);
     const int nb = cur.nb;
     const bool staged = nb >= 1 && nb <= 2;
     const int64_t a = slice * 32 + lane;
@@ -696,6 +707,7 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
         }
     }
     slice = next;
+    slice1 = slice2;
     cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
     cur.sbase = nxt.sbase; cur.width = nxt.width;
     nxt.sbase = nn.sbase; nxt.width = nn.width;
@@ -986,6 +998,8 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     int64_t blocks = (int64_t)per_sm * P->sm_count;
     const int64_t need = fem_div_up(P->n_slices, warps);
     if (blocks > need) blocks = need;
+    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8);
+    FEM_CUDA_CHECK(cudaMemsetAsync(A.slice_counter, 0, sizeof(unsigned long long), st));
     kern<<<(unsigned)blocks, warps * 32, smem, st>>>(A, M);
   }
   FEM_CUDA_CHECK(cudaGetLastError());
