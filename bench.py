@@ -324,7 +324,7 @@ def run_gpu(args):
         "metric": METRIC, "value": n_e_tot / (t_asm * 1e-3) / 1e6, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config 4: synthetic uniform P1 mesh {nx}x{nx * world} cells, {n_e_tot} elements "
+        "config": {"workload": f"config {4 if world == 1 else 5}: synthetic uniform P1 mesh {nx}x{nx * world} cells, {n_e_tot} elements "
                                f"({n_e_owned} per GPU, strip partition), DP return map + tangent assembly + PCG",
                    "n_elements": n_e_tot, "n_dof_per_gpu": n_dof_rank, "nnz_per_gpu": nnz_rank, "pcg_iters_per_step": args.pcg_iters,
                    "preconditioner": "jacobi", "plastic_fraction": float(rm["ind_p"].double().mean().item()),

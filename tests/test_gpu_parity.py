@@ -316,3 +316,90 @@ def test_assembly_variants_agree_bitwise(fem, golden):
         for a, b in zip(res[1], res[v]):
             assert np.array_equal(a, b), v
     assert_csr_bits(P.to_scipy_csr(fem["torch"].as_tensor(res[2][3]).cuda()), csr_from(g, "Kt"))
+
+
+def test_full_size_config4_properties(fem):
+    """BASELINE.json config 4 (N=2828, 15 995 168 elements): size-independent properties at the benchmarked size."""
+    torch = fem["torch"]
+    from fem_elastoplasticity_b200 import _lib, meshgen
+    from fem_elastoplasticity_b200.plan import dp_return_map
+    n = 2828
+    m = meshgen.square_mesh_p1(n, n)
+    d1, d2, wf = tables(fo.ElementType.P1)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    assert (P.n_e, P.n_n, P.n_dof, P.nnz) == (15995168, 8003241, 16006482, 224000228)      # SURVEY section 8
+    assert P.stage_info()[0] == 1
+    # row_ptr of a uniform mesh: every interior node has 7 neighbours
+    deg = (P.nbr_ptr[1:] - P.nbr_ptr[:-1])
+    assert int(deg.max()) == 7 and int(deg.min()) == 3
+    assert torch.equal(P.row_ptr[0::2][:-1].long(), 4 * P.nbr_ptr[:-1].long())
+    G, Kb, eta, c = meshgen.footing_materials(P.n_int)
+    kel = P.assemble_elastic(G, Kb)
+    # the oracle on the first rows of the mesh: bit-exact values on a 2828 x 2 strip (same numbering, same coordinates)
+    strip = fo.square_mesh_p1(n, 2, 10.0, 10.0 * 2 / n)
+    coord = m["coordinates"][:, : 3 * (n + 1)].cpu().numpy()
+    Ks = fo.canonical_csr(fo.elastic_stiffness(strip["elements"], coord, G[: 4 * n].cpu().numpy(), Kb[: 4 * n].cpu().numpy(), d1, d2, wf)[0])
+    rows = 2 * 2 * (n + 1)                                  # node rows 0 and 1 are complete in the strip
+    rp = P.row_ptr[: rows + 1].cpu().numpy()
+    sub = sp.csr_matrix((kel[: rp[-1]].cpu().numpy(), P.col_idx[: rp[-1]].cpu().numpy(), rp), shape=(rows, P.n_dof))
+    sub.eliminate_zeros()
+    ref = Ks[:rows]
+    assert np.array_equal(sub.indptr, ref.indptr) and np.array_equal(sub.indices, ref.indices) and np.array_equal(sub.data, ref.data)
+    # null space, symmetry, elastic-tangent identity, variant equality at full size
+    tx = torch.zeros(P.n_dof, dtype=torch.float64, device="cuda")
+    tx[1::2] = 1.0
+    assert P.spmv(kel, tx).abs().max().item() <= 1e-9 * kel.abs().max().item()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(P.n_dof, generator=g, dtype=torch.float64, device="cuda")
+    b = torch.randn(P.n_dof, generator=g, dtype=torch.float64, device="cuda")
+    ab, ba = torch.dot(b, P.spmv(kel, a)).item(), torch.dot(a, P.spmv(kel, b)).item()
+    assert abs(ab - ba) <= 1e-10 * abs(ab)
+    Es = meshgen.synthetic_strain(P.n_int)
+    r = dp_return_map(Es, None, G, Kb, eta, c)
+    counts = r["counts"].cpu().numpy()
+    assert counts.sum() == int(r["ind_p"].sum().item()) and counts[0] > 0 and counts[1] > 0
+    idx = slice(8000000, 8100000)
+    ref = fo.constitutive_problem(Es[:, idx].cpu().numpy(), np.zeros((4, 100000)), G[idx].cpu().numpy(), Kb[idx].cpu().numpy(),
+                                  eta[idx].cpu().numpy(), c[idx].cpu().numpy())
+    assert np.array_equal(r["ind_p"][idx].cpu().numpy().astype(bool), ref["ind_p"])
+    err = np.abs(r["s"][:, idx].cpu().numpy() - ref["s"]) / np.maximum(np.abs(ref["s"]), 1e-3 * np.abs(ref["s"]).max(axis=1, keepdims=True))
+    assert err.max() <= RTOL
+    kt = P.assemble_tangent(r["ds"])
+    try:
+        _lib.call("fem_set_tuning", b"assemble_variant", 2)
+        assert torch.equal(P.assemble_tangent(r["ds"]), kt)
+    finally:
+        _lib.call("fem_set_tuning", b"assemble_variant", 0)
+    r0 = dp_return_map(torch.zeros_like(Es), None, G, Kb, eta, c)
+    assert torch.equal(P.assemble_tangent(r0["ds"]), kel)
+
+
+def test_empty_and_ragged_inputs(fem):
+    """Edge cases: zero Gauss points, a single element, an isolated node, a node of valence > 8 (shared-memory kernel)."""
+    torch = fem["torch"]
+    api = fem["api"]
+    r = api.construct_constitutive_problem(np.zeros((3, 0)), np.zeros((4, 0)), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
+    assert r["s"].shape == (4, 0) and r["ds"].shape == (9, 0) and r["ind_p"].shape == (0,)
+    d1, d2, wf = tables(fo.ElementType.P1)
+    # one triangle + one node that belongs to no element (empty rows, as in the reference's B^T D B)
+    coord = np.array([[0.0, 1.0, 0.0, 5.0], [0.0, 0.0, 1.0, 5.0]])
+    elem = np.array([[0], [1], [2]])
+    P = fem["plan"].FemPlan(elem, coord, d1, d2, wf)
+    Ko = fo.canonical_csr(fo.elastic_stiffness(elem, coord, np.ones(1), 2 * np.ones(1), d1, d2, wf)[0])
+    K = P.to_scipy_csr(P.assemble_elastic(np.ones(1), 2 * np.ones(1)))
+    K.eliminate_zeros()
+    assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices) and np.array_equal(K.data, Ko.data)
+    assert K.indptr[-1] == K.indptr[6]                      # rows of the isolated node are empty
+    # a fan of 12 triangles around one node: valence 13 > 12 -> shared-memory accumulators
+    k = 12
+    ang = 2 * np.pi * np.arange(k) / k
+    coord = np.concatenate([[[0.0], [0.0]], np.array([np.cos(ang), np.sin(ang)]) * (1 + 0.1 * np.arange(k))], axis=1)
+    elem = np.array([[0] * k, list(range(1, k + 1)), [i % k + 1 for i in range(1, k + 1)]])
+    P = fem["plan"].FemPlan(elem, coord, d1, d2, wf)
+    assert P.max_degree == 13 and P.stage_info()[0] == 0
+    rng = np.random.default_rng(0)
+    G, Kb = 1 + rng.random(k), 2 + rng.random(k)
+    Ko = fo.canonical_csr(fo.elastic_stiffness(elem, coord, G, Kb, d1, d2, wf)[0])
+    K = P.to_scipy_csr(P.assemble_elastic(G, Kb))
+    K.eliminate_zeros()
+    assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices) and np.array_equal(K.data, Ko.data)
