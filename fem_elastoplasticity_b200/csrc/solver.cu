@@ -231,6 +231,33 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(int64_t n2, const dou
   if (blockIdx.x == 0 && threadIdx.x == 0) scal[3] = 0.0;  // p'Kp is re-accumulated by the next SpMV
 }
 
+// p-update fused with the halo push: the rows other ranks need are stored to their ghost rows (NVLink peer memory)
+// by the thread that computes them.  Offsets/counts are in doubles and even (whole nodes).
+__global__ void __launch_bounds__(256) pcg_update_p_push_kernel(int64_t n2, const double2* __restrict__ r, const double2* __restrict__ minv,
+                                                                double2* __restrict__ p, double* scal, int it, int64_t s0, int64_t c0,
+                                                                double2* dst0, int64_t s1, int64_t c1, double2* dst1) {
+  const double rz_old = scal[rz_old_slot(it)], rz_new = scal[rz_new_slot(it)];
+  const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 ri = r[i], mi = minv[i];
+    double2 pi = p[i];
+    pi.x = fma(beta, pi.x, mi.x * ri.x);
+    pi.y = fma(beta, pi.y, mi.y * ri.y);
+    p[i] = pi;
+    if (dst0 && i >= s0 && i < s0 + c0) dst0[i - s0] = pi;
+    if (dst1 && i >= s1 && i < s1 + c1) dst1[i - s1] = pi;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) scal[3] = 0.0;
+}
+
+__global__ void halo_push_kernel(const double2* __restrict__ v, int64_t s0, int64_t c0, double2* dst0, int64_t s1, int64_t c1,
+                                 double2* dst1) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c0 + c1; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < c0) { if (dst0) dst0[i] = v[s0 + i]; }
+    else if (dst1) dst1[i - c0] = v[s1 + (i - c0)];
+  }
+}
+
 static unsigned vec_grid(const int64_t n_items, const int sm_count) {
   int64_t b = (n_items + 255) / 256;
   const int64_t cap = (int64_t)(sm_count > 0 ? sm_count : 148) * 8;
@@ -357,6 +384,31 @@ extern "C" int fem_vec_axpby(int64_t n, double a, const double* x, double b, con
   FEM_REQUIRE(x && y && out && n >= 0, "null pointer");
   if (n == 0) return FEM_OK;
   axpby_kernel<<<vec_grid(n, sm_count_now()) * 4, 256, 0, (cudaStream_t)stream>>>(n, a, x, b, y, out);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_halo_push(const double* v, int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1,
+                             fem_stream stream) {
+  FEM_REQUIRE(v && src0 >= 0 && src1 >= 0 && n0 >= 0 && n1 >= 0 && src0 % 2 == 0 && src1 % 2 == 0 && n0 % 2 == 0 && n1 % 2 == 0,
+              "halo ranges must be whole nodes");
+  if ((!dst0 || n0 == 0) && (!dst1 || n1 == 0)) return FEM_OK;
+  const int64_t tot = (n0 + n1) / 2;
+  halo_push_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const double2*>(v), src0 / 2, n0 / 2, reinterpret_cast<double2*>(dst0), src1 / 2, n1 / 2,
+      reinterpret_cast<double2*>(dst1));
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_pcg_update_p_push(int64_t n, const double* r, const double* minv, double* p, double* scal, int iter,
+                                     int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1,
+                                     fem_stream stream) {
+  FEM_REQUIRE(r && minv && p && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
+  FEM_REQUIRE(src0 % 2 == 0 && src1 % 2 == 0 && n0 % 2 == 0 && n1 % 2 == 0, "halo ranges must be whole nodes");
+  pcg_update_p_push_kernel<<<vec_grid(n / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
+      n / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p), scal, iter,
+      src0 / 2, n0 / 2, reinterpret_cast<double2*>(dst0), src1 / 2, n1 / 2, reinterpret_cast<double2*>(dst1));
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

@@ -77,6 +77,47 @@ class StripPartition:
             dist.all_reduce(t)
 
 
+class PeerHalo:
+    """Halo exchange of the PCG search direction over NVLink peer memory (torch symmetric memory = CUDA IPC mappings).
+
+    ``p`` lives in a symmetric allocation; ``fem_pcg_update_p_push`` stores this rank's interface rows into the neighbours'
+    ghost rows from the kernel that computes them, and stream-ordered signals (put_signal / wait_signal) tell the neighbour
+    that its ghosts are current.  No spin-wait lives in our kernels.  Overwriting a neighbour's ghost rows is safe because the
+    all-reduce of {r'z, r'r} sits between every SpMV (the reader) and the next p update (the writer)."""
+    CHANNEL = 0
+
+    def __init__(self, part, n_dof_local, device):
+        import torch.distributed._symmetric_memory as symm
+        self.part = part
+        n_max = torch.tensor([n_dof_local], dtype=torch.int64, device=device)
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX)           # symmetric allocations have one size on every rank
+        self.buf = symm.empty(int(n_max.item()), dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.p = self.buf[:n_dof_local]
+        rd = part.row_dofs
+        ptrs = list(self.hdl.buffer_ptrs)
+        # (source offset, count, peer destination pointer) towards the upper and the lower neighbour
+        self.up = (part.last_owned_row * rd, rd, ptrs[part.rank + 1] + 0) if part.has_upper else (0, 0, 0)
+        self.lo = (part.first_owned_row * rd, rd, ptrs[part.rank - 1] + (part.ny_loc + 1) * rd * 8) if part.has_lower else (0, 0, 0)
+        self.hdl.barrier(channel=1)
+
+    def push_args(self):
+        return (self.up[0], self.up[1], C.c_void_p(self.up[2]), self.lo[0], self.lo[1], C.c_void_p(self.lo[2]))
+
+    def signal(self):
+        """After a push: tell both neighbours their ghost rows are written, then wait for theirs."""
+        part = self.part
+        if part.has_upper:
+            self.hdl.put_signal(part.rank + 1, self.CHANNEL)
+        if part.has_lower:
+            self.hdl.put_signal(part.rank - 1, self.CHANNEL)
+        if part.has_upper:
+            self.hdl.wait_signal(part.rank + 1, self.CHANNEL)
+        if part.has_lower:
+            self.hdl.wait_signal(part.rank - 1, self.CHANNEL)
+
+
 class CudaOps:
     """The PCG step kernels of the C ABI (include/fem_b200.h) on one plan."""
 
@@ -107,6 +148,13 @@ class CudaOps:
     def update_p(self, r, minv, p, scal, it):
         self._call("fem_pcg_update_p", self.n, self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), self._stream())
 
+    def update_p_push(self, r, minv, p, scal, it, push):
+        self._call("fem_pcg_update_p_push", self.n, self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), *push,
+                   self._stream())
+
+    def halo_push(self, v, push):
+        self._call("fem_halo_push", self._ptr(v), *push, self._stream())
+
     def spmv(self, k, x, y, mask, dot):
         self.plan.spmv(k, x, mask=mask, out=y, dot=dot)
 
@@ -115,11 +163,22 @@ class DistributedPCG:
     """Jacobi-PCG over a strip partition.  ``ops`` defaults to the CUDA kernels; the CPU tests inject a
     NumPy implementation of the same five steps to exercise partition + halo + reduction logic under gloo."""
 
-    def __init__(self, plan, part, mask, ops=None):
+    def __init__(self, plan, part, mask, ops=None, peer="auto"):
         self.part, self.mask = part, mask
         self.ops = ops if ops is not None else CudaOps(plan)
         o = self.ops
         self.r, self.p, self.q, self.x, self.minv = (o.new_vec() for _ in range(5))
+        # halo of p over NVLink peer memory when there are several CUDA ranks; NCCL send/recv otherwise / on failure
+        self.peer = None
+        if ops is None and part.world > 1 and peer in ("auto", True):
+            try:
+                self.peer = PeerHalo(part, self.ops.n, self.r.device)
+                self.p = self.peer.p
+            except Exception as e:                       # symmetric memory unavailable: keep the NCCL path
+                if peer is True:
+                    raise
+                self.peer_error = repr(e)
+                self.peer = None
         self.scal = o.new_vec(8)
         self.en = o.new_vec(3)
         self.owned = part.owned_mask(self.r.device)
@@ -135,13 +194,23 @@ class DistributedPCG:
         n_it = iters if iters is not None else maxit
         it = 0
         self.launches_last = 3
+        peer = self.peer
+        if peer is not None:                              # ghosts of the initial search direction
+            o.halo_push(self.p, peer.push_args())
+            peer.signal()
+            self.launches_last += 1
         while it < n_it:
-            part.halo_exchange(self.p)
+            if peer is None:
+                part.halo_exchange(self.p)
             o.spmv_dot(k_vals, self.p, self.q, self.mask, scal, it)
             part.all_reduce(scal[3:4])
             o.update_xr(self.p, self.q, self.minv, self.x, self.r, scal, it)
             part.all_reduce(scal[1:3] if it % 2 == 0 else scal[0:2])
-            o.update_p(self.r, self.minv, self.p, scal, it)
+            if peer is None:
+                o.update_p(self.r, self.minv, self.p, scal, it)
+            else:                                         # p update + halo push in one kernel, then stream-ordered signals
+                o.update_p_push(self.r, self.minv, self.p, scal, it, peer.push_args())
+                peer.signal()
             it += 1
             self.launches_last += 3
             if iters is None and it % check_every == 0:

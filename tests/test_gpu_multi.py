@@ -1,0 +1,84 @@
+"""Two-GPU test of the distributed PCG (NCCL halo and NVLink peer-memory halo): both must reproduce the single-GPU
+solve.  Skipped when fewer than two CUDA devices are visible (the driver's `pytest -m gpu` box has one)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nx, ny, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fem_elastoplasticity_b200 import meshgen
+    from fem_elastoplasticity_b200 import pythonFEM as api
+    from fem_elastoplasticity_b200.distributed import DistributedPCG, StripPartition
+    from fem_elastoplasticity_b200.plan import FemPlan
+    et = api.LagrangeElementType.P1
+    xi, wf = api.get_quadrature_volume(et)
+    _, d1, d2 = api.get_local_basis_volume(et, xi)
+    part = StripPartition(nx, ny, rank, world, size_x=10.0, size_y=10.0 * world)
+    mesh = part.local_mesh(dev)
+    P = FemPlan(mesh["elements"], mesh["coordinates"], d1, d2, wf, device=dev)
+    G, Kb, _, _ = meshgen.footing_materials(P.n_int, dev)
+    k = P.assemble_elastic(G, Kb)
+    mask = part.free_owned_mask(P, mesh)
+    b_global = np.random.default_rng(9).standard_normal(2 * (nx + 1) * (ny + 1))
+    lo = part.iy0 * part.row_dofs
+    rhs = torch.as_tensor(b_global[lo:lo + P.n_dof].copy()).to(dev)
+    res = {}
+    for name, peer in (("nccl", False), ("peer", True)):
+        pcg = DistributedPCG(P, part, mask, peer=peer)
+        x, its = pcg.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=25)
+        res[name] = x.cpu().numpy().copy()
+        res[name + "_its"] = its
+        res[name + "_is_peer"] = pcg.peer is not None
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, own=np.array(part.owned_dof_range()), **res)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_pcg_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    from fem_elastoplasticity_b200 import meshgen
+    from fem_elastoplasticity_b200 import pythonFEM as api
+    from fem_elastoplasticity_b200.plan import FemPlan
+    nx, ny, world = 96, 128, 2
+    mp.spawn(_worker, args=(world, _free_port(), nx, ny, str(tmp_path)), nprocs=world, join=True)
+    et = api.LagrangeElementType.P1
+    xi, wf = api.get_quadrature_volume(et)
+    _, d1, d2 = api.get_local_basis_volume(et, xi)
+    m = meshgen.square_mesh_p1(nx, ny, 10.0, 10.0 * world)
+    P = FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    G, Kb, _, _ = meshgen.footing_materials(P.n_int)
+    k = P.assemble_elastic(G, Kb)
+    b = np.random.default_rng(9).standard_normal(P.n_dof)
+    ref, its, rel = P.pcg(k, b, P.mask_u8(m["Q"]), rtol=1e-12, maxit=20000, check_every=25)
+    ref = ref.cpu().numpy()
+    for name in ("nccl", "peer"):
+        got = np.full_like(ref, np.nan)
+        for r in range(world):
+            d = np.load(tmp_path / f"r{r}.npz")
+            lo, (a, e) = int(d["lo"]), d["own"]
+            got[lo + a:lo + e] = d[name][a:e]
+            assert d[name + "_its"] > 0
+            if name == "peer":
+                assert bool(d["peer_is_peer"]), "symmetric-memory halo was not active"
+        assert not np.isnan(got).any()
+        np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
