@@ -235,10 +235,12 @@ __global__ void __launch_bounds__(256) pcg_update_p_kernel(int64_t n2, const dou
 // by the thread that computes them.  Offsets/counts are in doubles and even (whole nodes).
 __global__ void __launch_bounds__(256) pcg_update_p_push_kernel(int64_t n2, const double2* __restrict__ r, const double2* __restrict__ minv,
                                                                 double2* __restrict__ p, double* scal, int it, int64_t s0, int64_t c0,
-                                                                double2* dst0, int64_t s1, int64_t c1, double2* dst1) {
+                                                                double2* dst0, int64_t s1, int64_t c1, double2* dst1, int64_t own_lo) {
   const double rz_old = scal[rz_old_slot(it)], rz_new = scal[rz_new_slot(it)];
   const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+  // only the owned range [own_lo, n2) is updated: this rank's ghost rows are written by their owners' pushes, and a local
+  // write there would race with them
+  for (int64_t i = own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
     const double2 ri = r[i], mi = minv[i];
     double2 pi = p[i];
     pi.x = fma(beta, pi.x, mi.x * ri.x);
@@ -401,14 +403,14 @@ extern "C" int fem_halo_push(const double* v, int64_t src0, int64_t n0, double* 
   return FEM_OK;
 }
 
-extern "C" int fem_pcg_update_p_push(int64_t n, const double* r, const double* minv, double* p, double* scal, int iter,
-                                     int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1,
+extern "C" int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p, double* scal,
+                                     int iter, int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1,
                                      fem_stream stream) {
-  FEM_REQUIRE(r && minv && p && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
+  FEM_REQUIRE(r && minv && p && scal && own_lo >= 0 && own_hi > own_lo && own_lo % 2 == 0 && own_hi % 2 == 0, "null pointer or bad owned range");
   FEM_REQUIRE(src0 % 2 == 0 && src1 % 2 == 0 && n0 % 2 == 0 && n1 % 2 == 0, "halo ranges must be whole nodes");
-  pcg_update_p_push_kernel<<<vec_grid(n / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
-      n / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p), scal, iter,
-      src0 / 2, n0 / 2, reinterpret_cast<double2*>(dst0), src1 / 2, n1 / 2, reinterpret_cast<double2*>(dst1));
+  pcg_update_p_push_kernel<<<vec_grid((own_hi - own_lo) / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
+      own_hi / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p), scal, iter,
+      src0 / 2, n0 / 2, reinterpret_cast<double2*>(dst0), src1 / 2, n1 / 2, reinterpret_cast<double2*>(dst1), own_lo / 2);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

@@ -96,10 +96,13 @@ class PeerHalo:
         self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
         self.p = self.buf[:n_dof_local]
         rd = part.row_dofs
-        ptrs = list(self.hdl.buffer_ptrs)
+        n_sym = int(n_max.item())
+        # peer views of the same symmetric tensor (get_buffer accounts for the tensor's offset inside the allocation block)
+        self.peers = {r: self.hdl.get_buffer(r, (n_sym,), torch.float64) for r in (part.rank - 1, part.rank + 1) if 0 <= r < part.world}
         # (source offset, count, peer destination pointer) towards the upper and the lower neighbour
-        self.up = (part.last_owned_row * rd, rd, ptrs[part.rank + 1] + 0) if part.has_upper else (0, 0, 0)
-        self.lo = (part.first_owned_row * rd, rd, ptrs[part.rank - 1] + (part.ny_loc + 1) * rd * 8) if part.has_lower else (0, 0, 0)
+        self.up = (part.last_owned_row * rd, rd, self.peers[part.rank + 1].data_ptr()) if part.has_upper else (0, 0, 0)
+        self.lo = ((part.first_owned_row * rd, rd, self.peers[part.rank - 1].data_ptr() + (part.ny_loc + 1) * rd * 8)
+                   if part.has_lower else (0, 0, 0))
         self.hdl.barrier(channel=1)
 
     def push_args(self):
@@ -148,8 +151,8 @@ class CudaOps:
     def update_p(self, r, minv, p, scal, it):
         self._call("fem_pcg_update_p", self.n, self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), self._stream())
 
-    def update_p_push(self, r, minv, p, scal, it, push):
-        self._call("fem_pcg_update_p_push", self.n, self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), *push,
+    def update_p_push(self, own, r, minv, p, scal, it, push):
+        self._call("fem_pcg_update_p_push", int(own[0]), int(own[1]), self._ptr(r), self._ptr(minv), self._ptr(p), self._ptr(scal), int(it), *push,
                    self._stream())
 
     def halo_push(self, v, push):
@@ -209,7 +212,7 @@ class DistributedPCG:
             if peer is None:
                 o.update_p(self.r, self.minv, self.p, scal, it)
             else:                                         # p update + halo push in one kernel, then stream-ordered signals
-                o.update_p_push(self.r, self.minv, self.p, scal, it, peer.push_args())
+                o.update_p_push(part.owned_dof_range(), self.r, self.minv, self.p, scal, it, peer.push_args())
                 peer.signal()
             it += 1
             self.launches_last += 3

@@ -137,12 +137,13 @@ int fem_pcg_update_p(int64_t n, const double* r, const double* minv, double* p, 
 /* Multi-GPU variants over NVLink peer memory (one process per GPU; dst0/dst1 are the neighbours' ghost rows of the same
  * vector, mapped into this process by CUDA IPC / symmetric memory; NULL = no neighbour on that side).
  * fem_halo_push: dst0[0:n0] = v[src0:src0+n0], dst1[0:n1] = v[src1:src1+n1] (peer stores).
- * fem_pcg_update_p_push: fem_pcg_update_p fused with that push of the freshly computed p - the interface rows leave for the
- * neighbours from the kernel that produces them instead of through a separate send/recv.                      */
+ * fem_pcg_update_p_push: fem_pcg_update_p restricted to the owned DOF range [own_lo, own_hi) and fused with that push of the
+ * freshly computed p - the interface rows leave for the neighbours from the kernel that produces them instead of through
+ * a separate send/recv.  Ghost rows of p are never written locally (their owners push them).                  */
 int fem_halo_push(const double* v, int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1,
                   fem_stream stream);
-int fem_pcg_update_p_push(int64_t n, const double* r, const double* minv, double* p, double* scal, int iter, int64_t src0,
-                          int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1, fem_stream stream);
+int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p, double* scal, int iter,
+                          int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1, fem_stream stream);
 /* Single-GPU Jacobi-PCG on K[Q,Q] x[Q] = rhs[Q], x[~Q] left untouched at 0.  work: 4*n_dof doubles.
  * Stops when |r| <= rtol*|rhs| (checked every check_every iterations).  Synchronises.            */
 int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const uint8_t* free_mask, double rtol,
