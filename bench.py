@@ -194,7 +194,7 @@ def run_gpu(args):
     rm = {}
     k_tan, F = P.empty(P.nnz), P.empty(P.n_dof)
     k_el = P.assemble_elastic(G, Kb)
-    pcg = fdist.DistributedPCG(P, part, mask, peer={"auto": "auto", "nccl": False, "peer": True}[args.halo])
+    pcg = fdist.DistributedPCG(P, part, mask, peer={"auto": "auto", "nccl": False, "peer": True}[args.halo], use_graph=not args.no_graph)
     rhs = P.empty(P.n_dof)
     from fem_elastoplasticity_b200.plan import axpby
 
@@ -327,7 +327,7 @@ def run_gpu(args):
         "config": {"workload": f"config {4 if world == 1 else 5}: synthetic uniform P1 mesh {nx}x{nx * world} cells, {n_e_tot} elements "
                                f"({n_e_owned} per GPU, strip partition), DP return map + tangent assembly + PCG",
                    "n_elements": n_e_tot, "n_dof_per_gpu": n_dof_rank, "nnz_per_gpu": nnz_rank, "pcg_iters_per_step": args.pcg_iters,
-                   "preconditioner": "jacobi", "halo": ("nvlink peer stores fused into the p-update kernel (symmetric memory)" if pcg.peer is not None
+                   "preconditioner": "jacobi", "pcg_cuda_graph": bool(pcg.use_graph and pcg._graph is not None), "halo": ("nvlink peer stores fused into the p-update kernel (symmetric memory)" if pcg.peer is not None
                                                          else ("none (1 GPU)" if world == 1 else "nccl send/recv")), "plastic_fraction": float(rm["ind_p"].double().mean().item()),
                    "l2": "inputs larger than L2 (>=1 GB per array vs 126 MB), no flush needed",
                    "plan_build_s": t_plan, "plan_bytes": P.bytes},
@@ -364,7 +364,8 @@ def main():
     ap.add_argument("--cpu-nx", type=int, default=500, help="mesh side of the bounded CPU sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer"], help="multi-GPU halo exchange of the PCG")
+    ap.add_argument("--halo", default="nccl", choices=["auto", "nccl", "peer"], help="multi-GPU halo exchange of the PCG")
+    ap.add_argument("--no-graph", action="store_true", help="launch the PCG iterations eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -166,12 +166,15 @@ class DistributedPCG:
     """Jacobi-PCG over a strip partition.  ``ops`` defaults to the CUDA kernels; the CPU tests inject a
     NumPy implementation of the same five steps to exercise partition + halo + reduction logic under gloo."""
 
-    def __init__(self, plan, part, mask, ops=None, peer="auto"):
+    def __init__(self, plan, part, mask, ops=None, peer=False, use_graph=True):
         self.part, self.mask = part, mask
         self.ops = ops if ops is not None else CudaOps(plan)
         o = self.ops
         self.r, self.p, self.q, self.x, self.minv = (o.new_vec() for _ in range(5))
-        # halo of p over NVLink peer memory when there are several CUDA ranks; NCCL send/recv otherwise / on failure
+        # CUDA graph of an (even, odd) iteration pair: removes the per-launch host gaps of the ~7 launches per iteration
+        self.use_graph = bool(use_graph) and ops is None
+        self._graph, self._graph_key = None, None
+        # halo of p: NCCL send/recv (default; measured as fast at 8 GPUs) or NVLink peer stores fused into the p-update kernel
         self.peer = None
         if ops is None and part.world > 1 and peer in ("auto", True):
             try:
@@ -202,20 +205,30 @@ class DistributedPCG:
             o.halo_push(self.p, peer.push_args())
             peer.signal()
             self.launches_last += 1
-        while it < n_it:
+
+        def iteration(i):
             if peer is None:
                 part.halo_exchange(self.p)
-            o.spmv_dot(k_vals, self.p, self.q, self.mask, scal, it)
+            o.spmv_dot(k_vals, self.p, self.q, self.mask, scal, i)
             part.all_reduce(scal[3:4])
-            o.update_xr(self.p, self.q, self.minv, self.x, self.r, scal, it)
-            part.all_reduce(scal[1:3] if it % 2 == 0 else scal[0:2])
+            o.update_xr(self.p, self.q, self.minv, self.x, self.r, scal, i)
+            part.all_reduce(scal[1:3] if i % 2 == 0 else scal[0:2])
             if peer is None:
-                o.update_p(self.r, self.minv, self.p, scal, it)
+                o.update_p(self.r, self.minv, self.p, scal, i)
             else:                                         # p update + halo push in one kernel, then stream-ordered signals
-                o.update_p_push(part.owned_dof_range(), self.r, self.minv, self.p, scal, it, peer.push_args())
+                o.update_p_push(part.owned_dof_range(), self.r, self.minv, self.p, scal, i, peer.push_args())
                 peer.signal()
-            it += 1
-            self.launches_last += 3
+
+        graph = self._pair_graph(k_vals, iteration) if (self.use_graph and n_it >= 4) else None
+        while it < n_it:
+            if graph is not None and it % 2 == 0 and it + 2 <= n_it:
+                graph.replay()                            # iterations it (even) and it+1 (odd)
+                it += 2
+                self.launches_last += 6
+            else:
+                iteration(it)
+                it += 1
+                self.launches_last += 3
             if iters is None and it % check_every == 0:
                 h = scal.cpu()
                 if not torch.isfinite(h[1]):
@@ -224,6 +237,31 @@ class DistributedPCG:
                     break
         part.halo_exchange(self.x)
         return self.x, it
+
+    def _pair_graph(self, k_vals, iteration):
+        """CUDA graph of iterations (0, 1) - the kernels only depend on the parity of the iteration index.  Captured after
+        one eager pair (NCCL communicators / lazy initialisation must not happen under capture); cached per matrix buffer."""
+        key = (k_vals.data_ptr(), self.p.data_ptr())
+        if self._graph is not None and self._graph_key == key:
+            return self._graph
+        try:
+            saved = [t.clone() for t in (self.x, self.r, self.p, self.q, self.scal)]
+            iteration(0)
+            iteration(1)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                iteration(0)
+                iteration(1)
+            for t, sv in zip((self.x, self.r, self.p, self.q, self.scal), saved):
+                t.copy_(sv)                               # the warm-up and the capture must not advance the solve
+            torch.cuda.synchronize()
+            self._graph, self._graph_key = g, key
+        except Exception as e:                            # capture unsupported in this configuration: eager launches
+            self.graph_error = repr(e)
+            self.use_graph = False
+            self._graph = None
+        return self._graph
 
     def energy_norms(self, k_vals, v0, v1, v2):
         """v_i' K v_i over the whole (distributed) DOF set; returns a device tensor of 3 doubles."""

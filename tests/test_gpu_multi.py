@@ -41,8 +41,8 @@ def _worker(rank, world, port, nx, ny, out_dir):
     lo = part.iy0 * part.row_dofs
     rhs = torch.as_tensor(b_global[lo:lo + P.n_dof].copy()).to(dev)
     res = {}
-    for name, peer in (("nccl", False), ("peer", True)):
-        pcg = DistributedPCG(P, part, mask, peer=peer)
+    for name, peer, graph in (("nccl", False, True), ("peer", True, True), ("eager", False, False)):
+        pcg = DistributedPCG(P, part, mask, peer=peer, use_graph=graph)
         x, its = pcg.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=25)
         res[name] = x.cpu().numpy().copy()
         res[name + "_its"] = its
@@ -71,7 +71,7 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
     b = np.random.default_rng(9).standard_normal(P.n_dof)
     ref, its, rel = P.pcg(k, b, P.mask_u8(m["Q"]), rtol=1e-12, maxit=20000, check_every=25)
     ref = ref.cpu().numpy()
-    for name in ("nccl", "peer"):
+    for name in ("nccl", "peer", "eager"):
         got = np.full_like(ref, np.nan)
         for r in range(world):
             d = np.load(tmp_path / f"r{r}.npz")
@@ -82,3 +82,30 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
                 assert bool(d["peer_is_peer"]), "symmetric-memory halo was not active"
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+
+
+def test_single_rank_graph_pcg_matches_c_loop():
+    """World size 1: the Python-sequenced PCG (CUDA-graph replay of iteration pairs, and eager) equals fem_pcg."""
+    import torch
+    from fem_elastoplasticity_b200 import meshgen
+    from fem_elastoplasticity_b200 import pythonFEM as api
+    from fem_elastoplasticity_b200.distributed import DistributedPCG, StripPartition
+    from fem_elastoplasticity_b200.plan import FemPlan
+    nx, ny = 64, 80
+    et = api.LagrangeElementType.P1
+    xi, wf = api.get_quadrature_volume(et)
+    _, d1, d2 = api.get_local_basis_volume(et, xi)
+    part = StripPartition(nx, ny, 0, 1)
+    mesh = part.local_mesh("cuda")
+    P = FemPlan(mesh["elements"], mesh["coordinates"], d1, d2, wf)
+    G, Kb, _, _ = meshgen.footing_materials(P.n_int)
+    k = P.assemble_elastic(G, Kb)
+    mask = part.free_owned_mask(P, mesh)
+    b = torch.as_tensor(np.random.default_rng(4).standard_normal(P.n_dof)).cuda()
+    ref, its, rel = P.pcg(k, b, mask, rtol=0.0, maxit=200, check_every=200, raise_on_maxit=False)
+    for graph in (True, False):
+        pcg = DistributedPCG(P, part, mask, use_graph=graph)
+        x, n_it = pcg.solve(k, b.clone(), iters=200)
+        assert n_it == 200
+        assert (pcg._graph is not None) == graph
+        np.testing.assert_allclose(x.cpu().numpy(), ref.cpu().numpy(), rtol=1e-9, atol=1e-12 * float(ref.abs().max()))
