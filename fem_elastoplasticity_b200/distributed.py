@@ -171,8 +171,10 @@ class DistributedPCG:
         self.ops = ops if ops is not None else CudaOps(plan)
         o = self.ops
         self.r, self.p, self.q, self.x, self.minv = (o.new_vec() for _ in range(5))
-        # CUDA graph of an (even, odd) iteration pair: removes the per-launch host gaps of the ~7 launches per iteration
-        self.use_graph = bool(use_graph) and ops is None
+        # CUDA graph of an (even, odd) iteration pair: removes the per-launch host gaps.  Single rank only: with NCCL
+        # send/recv + all-reduces captured inside the graph a full-size 2-GPU run hung (round-1 finding), so multi-rank
+        # runs launch eagerly.
+        self.use_graph = bool(use_graph) and ops is None and part.world == 1
         self._graph, self._graph_key = None, None
         # halo of p: NCCL send/recv (default; measured as fast at 8 GPUs) or NVLink peer stores fused into the p-update kernel
         self.peer = None
