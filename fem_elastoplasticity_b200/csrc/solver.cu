@@ -107,7 +107,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
   int unroll = g_fem_tuning.spmv_unroll;
   if (unroll != 1 && unroll != 2 && unroll != 4) unroll = 2;
   int64_t blocks = (P->n_n * group / unroll + threads - 1) / threads;
-  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 32);  // bounded grid: few dot-product atomics
+  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 8);  // persistent grid (measured best), few dot-product atomics
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
 #define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<(unsigned)blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b)

@@ -403,3 +403,41 @@ def test_empty_and_ragged_inputs(fem):
     K = P.to_scipy_csr(P.assemble_elastic(G, Kb))
     K.eliminate_zeros()
     assert np.array_equal(K.indptr, Ko.indptr) and np.array_equal(K.indices, Ko.indices) and np.array_equal(K.data, Ko.data)
+
+
+def test_transform_and_csv_fixture_io(fem, golden, tmp_path):
+    """transform() on the device; CSV mesh reader and the golden *_qq.csv / fq.csv layout."""
+    from fem_elastoplasticity_b200 import fixture_io
+    m, g = golden("assembly_tsx_p1.npz"), golden("tsx_csv_golden.npz")
+    np.savetxt(tmp_path / "coord.csv", m["coordinates"], delimiter=",", fmt="%.17g")
+    np.savetxt(tmp_path / "elem.csv", m["elements"] + 1, delimiter=",", fmt="%d")
+    coords, elem = fixture_io.read_mesh_csv(tmp_path / "coord.csv", tmp_path / "elem.csv")
+    assert np.array_equal(coords, m["coordinates"]) and np.array_equal(elem, m["elements"])
+    d1, d2, wf = tables(fo.ElementType.P1)
+    n_e = elem.shape[1]
+    G, Kb = float(m["shear"]) * np.ones(n_e), float(m["bulk"]) * np.ones(n_e)
+    K, B, w, i_d, j_d, D = fem["api"].get_elastic_stiffness_matrix(elem, coords, G, Kb, d1, d2, wf)
+    q = fixture_io.tsx_dirichlet_mask(coords)
+    assert np.array_equal(q, fo.tsx_q_mask(coords))
+    # regenerate the missing kelast_qq.csv and read it back; for P1 it must carry k_tangent_qq.csv's pattern
+    fixture_io.write_qq_csv(tmp_path / "kelast_qq.csv", K, q)
+    kqq = fixture_io.read_qq_csv(tmp_path / "kelast_qq.csv")
+    assert kqq.shape == tuple(g["kqq_shape"]) == (908, 908)
+    assert np.array_equal(kqq, fixture_io.free_block(K, q))           # %.17g round-trips doubles
+    ref = csr_from(g, "kqq", shape=(908, 908))
+    got = sp.csr_matrix(kqq)
+    got.sort_indices()
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    assert np.abs(got.data - ref.data).max() <= 2e-4 * np.abs(ref.data).max()
+    # F[Q] export layout
+    _, _, _, _, s0, _ = fo.tsx_constants()
+    F0 = fem["api"].internal_force(B, np.tile(s0, (1, n_e)))
+    fixture_io.write_fq_csv(tmp_path / "f0q.csv", F0, q)
+    back = np.genfromtxt(tmp_path / "f0q.csv", delimiter=",")
+    assert back.shape == (908,) and np.array_equal(back, F0.ravel()[q.flatten(order="F")])
+    # transform(): integration-point -> nodal weighted average (Plasticity2D_DP/pythonFEM.py:760-816)
+    P = K._fem_plan
+    rng = np.random.default_rng(2)
+    qi = rng.standard_normal(n_e)
+    got = P.transform(qi).cpu().numpy()
+    np.testing.assert_allclose(got, fo.transform(qi, elem, w), rtol=1e-13)
