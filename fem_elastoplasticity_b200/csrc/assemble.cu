@@ -998,7 +998,9 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     int64_t blocks = (int64_t)per_sm * P->sm_count;
     const int64_t need = fem_div_up(P->n_slices, warps);
     if (blocks > need) blocks = need;
-    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8);
+    // one of 8 counters, round-robin per launch, so launches of the same plan on different streams never share one
+    static unsigned launch_no = 0;
+    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8) + (launch_no++ & 7u);
     FEM_CUDA_CHECK(cudaMemsetAsync(A.slice_counter, 0, sizeof(unsigned long long), st));
     kern<<<(unsigned)blocks, warps * 32, smem, st>>>(A, M);
   }
