@@ -178,7 +178,11 @@ def run_gpu(args):
     xi, wf = api.get_quadrature_volume(et)
     _, d1, d2 = api.get_local_basis_volume(et, xi)
     # weak scaling: rank r owns cell rows [r*nx, (r+1)*nx) of an nx x (nx*world) mesh plus one ghost cell row per neighbour
-    part = fdist.StripPartition(nx, nx * world, rank, world, size_x=10.0, size_y=10.0 * world)
+    if args.scaling == "strong":   # fixed total mesh (~nx x nx cells, rows rounded up to a multiple of the rank count)
+        ny_global = -(-nx // world) * world
+    else:                          # weak: nx x nx cells per GPU
+        ny_global = nx * world
+    part = fdist.StripPartition(nx, ny_global, rank, world, size_x=10.0, size_y=10.0 * ny_global / nx)
     mesh = part.local_mesh(dev)
     t_plan0 = time.perf_counter()
     P = FemPlan(mesh["elements"], mesh["coordinates"], d1, d2, wf, device=dev)
@@ -331,9 +335,9 @@ def run_gpu(args):
                                   ("criterion(3 spmv)", "spmv", t_crit / 3.0))}
     line = {
         "metric": METRIC, "value": n_e_tot / (t_asm * 1e-3) / 1e6, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config {4 if world == 1 else 5}: synthetic uniform P1 mesh {nx}x{nx * world} cells, {n_e_tot} elements "
+        "config": {"workload": f"config {4 if (world == 1 or args.scaling == 'strong') else 5}: synthetic uniform P1 mesh {nx}x{ny_global} cells, {n_e_tot} elements "
                                f"({n_e_owned} per GPU, strip partition), DP return map + tangent assembly + PCG",
                    "n_elements": n_e_tot, "n_dof_per_gpu": n_dof_rank, "nnz_per_gpu": nnz_rank, "pcg_iters_per_step": args.pcg_iters,
                    "preconditioner": "jacobi", "pcg_cuda_graph": bool(pcg.use_graph and pcg._graph is not None), "halo": ("nvlink peer stores fused into the p-update kernel (symmetric memory)" if pcg.peer is not None
@@ -373,6 +377,8 @@ def main():
     ap.add_argument("--pcg-iters", type=int, default=50)
     ap.add_argument("--cpu-nx", type=int, default=500, help="mesh side of the bounded CPU sample")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: nx x nx cells per GPU (config 5 at 8 GPUs); strong: one nx x nx mesh split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="nccl", choices=["auto", "nccl", "peer"], help="multi-GPU halo exchange of the PCG")
     ap.add_argument("--no-graph", action="store_true", help="launch the PCG iterations eagerly instead of replaying a CUDA graph")

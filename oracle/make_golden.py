@@ -175,6 +175,20 @@ def main():
         allt.update(pack(f"{name}_K", canon(Ka)))
         allt.update(pack(f"{name}_S", structural(Ba, Da)))
     np.savez_compressed(os.path.join(OUT, "assembly_all_types_l0.npz"), **allt)
+    # -- 8. tsx-tunnel P2: mesh from the reference's own create_midpoints (:1508-1633), K and F0 = B^T (w sigma0) (:1737);
+    #        F0[Q] is what the reference's f0q.csv holds (3594 free DOFs)
+    d = rt.create_midpoints(rt.LagrangeElementType.P2, coords, elem)
+    ce, ee = d["coord_ext"], d["elem_ext"].astype(np.int64)
+    P2 = rt.LagrangeElementType.P2
+    x2, w2 = rt.get_quadrature_volume(P2)
+    _, b1, b2 = rt.get_local_basis_volume(P2, x2)
+    ni = ee.shape[1] * np.size(w2)
+    g_tsx, k_tsx = 60000 / (2 * 1.2), 60000 / (3 * (1 - 2 * 0.2))
+    K2, B2, wt2, _, _, _ = rt.get_elastic_stiffness_matrix(ee, ce, g_tsx * np.ones(ni), k_tsx * np.ones(ni), b1, b2, w2)
+    s0 = np.array([-45, -11, 0, -60]).reshape((-1, 1), order="F")
+    F0 = B2.T @ np.reshape(np.tile(wt2.flatten(order="F"), (3, 1)) * s0[0:3, :], (3 * ni, 1), order="F")
+    np.savez_compressed(os.path.join(OUT, "assembly_tsx_p2.npz"), coordinates=ce, elements=ee, shear=g_tsx, bulk=k_tsx, weight=wt2,
+                        F0=np.asarray(F0).ravel(), **pack("K", canon(K2)))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -441,3 +441,28 @@ def test_transform_and_csv_fixture_io(fem, golden, tmp_path):
     qi = rng.standard_normal(n_e)
     got = P.transform(qi).cpu().numpy()
     np.testing.assert_allclose(got, fo.transform(qi, elem, w), rtol=1e-13)
+
+
+def test_tsx_p2_unstructured(fem, golden):
+    """P2 kernels (6 nodes, 7 points, shared-memory accumulators) on the unstructured tsx mesh: K bit-exact vs the reference,
+    F0 = B^T (w sigma0) bit-exact, and F0[Q] against the reference's own f0q.csv."""
+    g, c = golden("assembly_tsx_p2.npz"), golden("tsx_csv_golden.npz")
+    et = fo.ElementType.P2
+    d1, d2, wf = tables(et)
+    P = fem["plan"].FemPlan(g["elements"], g["coordinates"], d1, d2, wf)
+    assert (P.n_p, P.n_q, P.n_n) == (6, 7, 1839) and P.max_degree > 12
+    assert np.array_equal(P.weight.cpu().numpy(), g["weight"].flatten(order="F"))
+    vals = P.assemble_elastic(float(g["shear"]) * np.ones(P.n_int), float(g["bulk"]) * np.ones(P.n_int))
+    assert_csr_bits(P.to_scipy_csr(vals), csr_from(g, "K"))
+    s0 = fo.tsx_constants()[4]
+    F0 = P.internal_force(np.tile(s0, (1, P.n_int))).cpu().numpy()
+    assert np.array_equal(F0, g["F0"])
+    qf = fo.tsx_q_mask(g["coordinates"]).flatten(order="F")
+    assert np.abs(F0[qf] - c["f0q"]).max() < 2e-3
+    # strain of a linear field is constant on quadratic elements too
+    u = np.empty(P.n_dof)
+    u[0::2] = 1e-3 * g["coordinates"][0] - 2e-3 * g["coordinates"][1]
+    u[1::2] = 4e-3 * g["coordinates"][0] + 5e-4 * g["coordinates"][1]
+    E = P.strain(u).cpu().numpy()
+    for row, val in zip(E, (1e-3, 5e-4, -2e-3 + 4e-3)):
+        assert np.abs(row - val).max() <= 1e-11
