@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
 // On structured meshes all lanes of a warp take the same case (same local topology) so the branch is
 // warp-uniform; on irregular meshes the cases serialise but stay correct.  No shared memory: the whole
 // 228 KB stay L1, which is what serves the re-reads of an element's DS/dphi by its three nodes.
-template <int NP, int NQ, int MODE, bool FORCE, int MAXDEG, bool PIPE, int MINB>
-__global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmArgs A) {
+template <int NP, int NQ, int MODE, bool FORCE, int MAXDEG>
+__global__ void __launch_bounds__(128) assemble_rows_reg_kernel(const AsmArgs A) {
   constexpr int MW = (NP + 1 + 3) / 4;
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t slice = a >> 5;
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
   const int64_t sbase = A.slice_ptr[slice];
   const int width = (int)((A.slice_ptr[slice + 1] - sbase) >> 5);
   double f0 = 0.0, f1 = 0.0;
-  // Software pipeline: the incidence keys/metadata of a whole chunk are fetched up front (one latency instead
-  // of one per incidence) and the element data of incidence i+1 is in flight while incidence i is accumulated.
+  // The incidence keys/metadata of a whole chunk are fetched up front (one memory latency instead of one per incidence).
+  // Double-buffering the element data as well was measured slower: register pressure costs more occupancy than it hides.
   constexpr int CH = 8;
   using PD = PointData<NP, MODE, FORCE>;
   for (int c0 = 0; c0 < width; c0 += CH) {
@@ -220,11 +220,10 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
         for (int w = 0; w < MW; ++w) metas[i][w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
       }
     }
-    PD cur, nxt;
-    if (PIPE && keys[0] != FEM_INVALID_KEY) load_point<NP, MODE, FORCE>(A, (int64_t)(keys[0] >> 3) * NQ, cur);
+    PD cur;
     const int n_it = (width - c0) < CH ? (width - c0) : CH;
 #pragma unroll 1
-    for (int i = 0; i < n_it; ++i) {  // rolled: keys[0] is the current incidence, keys[1] the next (register queue)
+    for (int i = 0; i < n_it; ++i) {  // rolled: keys[0] is the current incidence (register queue)
       const uint32_t key = keys[0];
       const bool valid = key != FEM_INVALID_KEY;
       const int64_t e = key >> 3;
@@ -234,14 +233,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
       for (int w = 0; w < MW; ++w) meta[w] = metas[0][w];
 #pragma unroll 1
       for (int q = 0; q < NQ; ++q) {
-        // prefetch the next point: next quadrature point of this element, else the first of the next incidence
-        if (!PIPE) {
-          if (valid) load_point<NP, MODE, FORCE>(A, e * NQ + q, cur);
-        } else if (q + 1 < NQ) {
-          if (valid) load_point<NP, MODE, FORCE>(A, e * NQ + q + 1, nxt);
-        } else if (i + 1 < n_it && keys[1] != FEM_INVALID_KEY) {
-          load_point<NP, MODE, FORCE>(A, (int64_t)(keys[1] >> 3) * NQ, nxt);
-        }
+        if (valid) load_point<NP, MODE, FORCE>(A, e * NQ + q, cur);
         if (valid) {
           double tx[3], ty[3];
           point_terms<NP, MODE, FORCE>(A, cur, la, tx, ty, f0, f1);
@@ -269,7 +261,6 @@ __global__ void __launch_bounds__(128, MINB) assemble_rows_reg_kernel(const AsmA
 #undef FEM_UPD
           }
         }
-        if (PIPE) cur = nxt;
       }
 #pragma unroll
       for (int k = 0; k + 1 < CH; ++k) {  // shift the key queue
@@ -716,223 +707,6 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
   }
 }
 
-// ---- variant E: persistent TMA staging, one node ROW per thread -------------------------------------------------
-// Variant D is starved for warps: 64 accumulator registers per thread and ~20 KB of staged boxes per warp allow only
-// ~10 warps per SM.  Here a PAIR of warps shares the two staged boxes of a slice; warp r of the pair owns CSR row
-// 2a + r of each of the slice's 32 nodes (16 accumulator doubles per thread).  Every K entry is still produced by
-// the same operations in the same order, so the result is bit-identical; occupancy roughly doubles.
-__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory"); }
-
-template <int MODE, bool FORCE, int MAXDEG, int NPAIR, int MINB>
-__global__ void __launch_bounds__(64 * NPAIR, MINB) assemble_rows_tmap2_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
-  using L = StageLayout<MODE, FORCE>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, r = warp & 1;  // r: which of the node's two rows this warp owns
-  const bool leader = (r == 0) && (lane == 0);
-  const int bw = A.boxw;
-  unsigned char* wbase = smem_raw + (size_t)pair * L::warp_b(bw);
-  unsigned char* box0 = wbase;
-  unsigned char* box1 = wbase + L::box_b(bw);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * L::box_b(bw));
-  const uint32_t bar0 = smem_u32(mbar), bar1 = smem_u32(mbar + 1);
-  if (leader) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(1));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar1), "r"(1));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  pair_sync(pair);
-  const int64_t n_pairs = (int64_t)gridDim.x * NPAIR;
-  const int64_t n_slices = A.n_slices;
-  int64_t slice = (int64_t)blockIdx.x * NPAIR + pair;
-  uint32_t ph0 = 0, ph1 = 0;
-  constexpr int CH = 8;
-  struct Book { int nb, st0, st1, deg, width; int64_t base, sbase; };
-  auto load_box = [&](int64_t s, Book& k) {
-    k.nb = 0; k.st0 = 0; k.st1 = 0;
-    if (s < n_slices) { k.nb = A.stage_box[s * 3]; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2]; }
-  };
-  auto load_node = [&](int64_t s, Book& k) {
-    k.deg = 0; k.base = 0;
-    const int64_t a = s * 32 + lane;
-    if (s < n_slices && a < A.n_n) {
-      const int nbp = A.nbr_ptr[a];
-      k.deg = A.nbr_ptr[a + 1] - nbp;
-      k.base = 4 * (int64_t)nbp;
-    }
-  };
-  auto load_sell = [&](int64_t s, Book& k) {
-    k.sbase = 0; k.width = 0;
-    if (s < n_slices) { k.sbase = A.slice_ptr[s]; k.width = (int)((A.slice_ptr[s + 1] - k.sbase) >> 5); }
-  };
-  Book cur, nxt;
-  uint32_t words[CH], nwords[CH];
-  load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
-  load_sell(slice + n_pairs, nxt);
-#pragma unroll
-  for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
-  if (slice < n_slices && leader && cur.nb >= 1 && cur.nb <= 2) {
-    issue_box<MODE, FORCE>(M, box0, bw, cur.st0, bar0);
-    if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
-  }
-  while (slice < n_slices) {  // pair-uniform
-    const int64_t next = slice + n_pairs;
-    load_box(next, nxt);
-    load_node(next, nxt);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) nwords[i] = (i < nxt.width) ? __ldcs(A.inc_stage + nxt.sbase + (int64_t)i * 32 + lane) : 0u;
-    Book nn;
-    load_sell(next + n_pairs, nn);
-    const int nb = cur.nb;
-    const bool staged = nb >= 1 && nb <= 2;
-    const int64_t a = slice * 32 + lane;
-    double acc[MAXDEG][2];
-#pragma unroll
-    for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = 0.0;
-    double f = 0.0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      if (staged) {
-        if (pass == 0) { mbar_wait(bar0, ph0); ph0 ^= 1; }
-        else if (nb == 2) { mbar_wait(bar1, ph1); ph1 ^= 1; }
-      }
-      if (pass == 0 || (staged && nb == 2)) {
-#pragma unroll 1
-        for (int i = 0; i < CH; ++i) {
-          const uint32_t word = words[0];
-#pragma unroll
-          for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
-          words[CH - 1] = word;
-          if (!(word & 0x80000000u)) continue;
-          const int li = word & 0x1FF;
-          if (staged && ((li >= bw) != (pass == 1))) continue;
-          const int la = (word >> 9) & 3;
-          // data of this (element, point): weight, dphi of the 3 nodes, the 6 D entries and 2 stresses row r needs
-          double w, d1[3], d2[3], Dr[3], D2[3], sr = 0.0, s2 = 0.0;
-          if (staged) {
-            const int o = li - pass * bw;
-            const unsigned char* bb = pass ? box1 : box0;
-            const double* g = reinterpret_cast<const double*>(bb) + o;
-            w = g[0];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { d1[p] = g[(1 + p) * bw]; d2[p] = g[(4 + p) * bw]; }
-            bb += L::geom_b(bw);
-            const double* t0 = reinterpret_cast<const double*>(bb) + o;
-            if (MODE == MODE_ELASTIC) {
-              const double G = t0[0], Kb = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                Dr[c] = (A.dev2[r + 3 * c] * G + A.vol[r + 3 * c] * Kb) * w;
-                D2[c] = (A.dev2[2 + 3 * c] * G + A.vol[2 + 3 * c] * Kb) * w;
-              }
-            } else {
-              double G = 0.0, Kb = 0.0;
-              if (MODE == MODE_TANGENT_REF) {
-                G = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
-                Kb = (reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw)) + o)[0];
-              }
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const double a_r = w * t0[(r + 3 * c) * bw], a_2 = w * t0[(2 + 3 * c) * bw];
-                if (MODE == MODE_TANGENT_REF) {
-                  Dr[c] = a_r - (A.dev2[r + 3 * c] * G + A.vol[r + 3 * c] * Kb) * w;
-                  D2[c] = a_2 - (A.dev2[2 + 3 * c] * G + A.vol[2 + 3 * c] * Kb) * w;
-                } else {
-                  Dr[c] = a_r;
-                  D2[c] = a_2;
-                }
-              }
-            }
-            if (FORCE) {
-              const double* sp = reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw) + L::t2_b(bw)) + o;
-              sr = sp[r * bw];
-              s2 = sp[2 * bw];
-            }
-          } else {  // direct loads (slices with more than two boxes)
-            const int64_t g = (int64_t)(A.inc_key[cur.sbase + (int64_t)i * 32 + lane] >> 3), n_int = A.n_int;
-            w = A.weight[g];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) { d1[p] = A.dphi1[(int64_t)p * n_int + g]; d2[p] = A.dphi2[(int64_t)p * n_int + g]; }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              if (MODE == MODE_ELASTIC) {
-                const double G = A.shear[g], Kb = A.bulk[g];
-                Dr[c] = (A.dev2[r + 3 * c] * G + A.vol[r + 3 * c] * Kb) * w;
-                D2[c] = (A.dev2[2 + 3 * c] * G + A.vol[2 + 3 * c] * Kb) * w;
-              } else {
-                const double a_r = w * A.DS[(int64_t)(r + 3 * c) * n_int + g], a_2 = w * A.DS[(int64_t)(2 + 3 * c) * n_int + g];
-                if (MODE == MODE_TANGENT_REF) {
-                  const double G = A.shear[g], Kb = A.bulk[g];
-                  Dr[c] = a_r - (A.dev2[r + 3 * c] * G + A.vol[r + 3 * c] * Kb) * w;
-                  D2[c] = a_2 - (A.dev2[2 + 3 * c] * G + A.vol[2 + 3 * c] * Kb) * w;
-                } else {
-                  Dr[c] = a_r;
-                  D2[c] = a_2;
-                }
-              }
-            }
-            if (FORCE) { sr = A.S[(int64_t)r * n_int + g]; s2 = A.S[2 * n_int + g]; }
-          }
-          double d1a = d1[0], d2a = d2[0];
-          if (la == 1) { d1a = d1[1]; d2a = d2[1]; }
-          if (la == 2) { d1a = d1[2]; d2a = d2[2]; }
-          // row r of B_a^T: x-dof (d1a, 0, d2a), y-dof (0, d2a, d1a)  ->  t_c = u*D[r][c] + v*D[2][c]
-          const double u = r ? d2a : d1a, v = r ? d1a : d2a;
-          if (FORCE) f = (f + u * (w * sr)) + v * (w * s2);   // F[2a+r]: rows 3g+r and 3g+2 of B^T (w s)
-          double t[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) t[c] = u * Dr[c] + v * D2[c];
-#pragma unroll
-          for (int lb = 0; lb < 3; ++lb) {
-            const int slot = (word >> (11 + 4 * lb)) & 15;
-            const double b1 = d1[lb], b2 = d2[lb];
-            const double p00 = t[0] * b1, p01 = t[2] * b2, p10 = t[1] * b2, p11 = t[2] * b1;
-#define FEM_UPD(J)                               \
-  case J:                                        \
-    if (J < MAXDEG) {                            \
-      acc[J < MAXDEG ? J : 0][0] = (acc[J < MAXDEG ? J : 0][0] + p00) + p01; \
-      acc[J < MAXDEG ? J : 0][1] = (acc[J < MAXDEG ? J : 0][1] + p10) + p11; \
-    }                                            \
-    break;
-            switch (slot) {
-              FEM_UPD(0) FEM_UPD(1) FEM_UPD(2) FEM_UPD(3) FEM_UPD(4) FEM_UPD(5) FEM_UPD(6) FEM_UPD(7)
-              default: break;
-            }
-#undef FEM_UPD
-          }
-        }
-      }
-      pair_sync(pair);  // both warps are done reading this pass's box
-      if (leader && nxt.nb >= 1 && nxt.nb <= 2) {
-        if (pass == 0) issue_box<MODE, FORCE>(M, box0, bw, nxt.st0, bar0);
-        else if (nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
-      }
-    }
-    if (a < A.n_n) {
-      const int deg = cur.deg;
-      if (FORCE) A.F[2 * a + r] = f;
-      double2* row = reinterpret_cast<double2*>(A.K_vals + cur.base) + r * deg;
-#pragma unroll
-      for (int j = 0; j < MAXDEG; ++j)
-        if (j < deg) {
-          double2 v0 = make_double2(acc[j][0], acc[j][1]);
-          if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction
-            const double2 k0 = reinterpret_cast<const double2*>(A.Kel + cur.base)[r * deg + j];
-            v0.x = k0.x + v0.x;
-            v0.y = k0.y + v0.y;
-          }
-          __stcs(row + j, v0);
-        }
-    }
-    slice = next;
-    cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
-    cur.sbase = nxt.sbase; cur.width = nxt.width;
-    nxt.sbase = nn.sbase; nxt.width = nn.width;
-#pragma unroll
-    for (int i = 0; i < CH; ++i) words[i] = nwords[i];
-  }
-}
-
 template <int MODE, bool FORCE>
 static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   using L = StageLayout<MODE, FORCE>;
@@ -960,22 +734,7 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   int warps = 4;
   size_t smem = (size_t)warps * L::warp_b(bw);
   if (smem > 227 * 1024) return -1;
-  if (g_fem_tuning.assemble_variant == 8 || g_fem_tuning.assemble_variant == 9) {
-    // persistent, one row per thread; variant 9 = no register cap (2 CTAs/SM), default = capped for 3 CTAs/SM
-    constexpr int NPAIR = 3;
-    const bool capped = g_fem_tuning.assemble_variant != 9;
-    void (*kern)(const AsmArgs, const StageMaps) = capped ? assemble_rows_tmap2_kernel<MODE, FORCE, 8, NPAIR, 3>
-                                                         : assemble_rows_tmap2_kernel<MODE, FORCE, 8, NPAIR, 1>;
-    smem = (size_t)NPAIR * L::warp_b(bw);
-    FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    FEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64 * NPAIR, smem));
-    if (per_sm < 1) return -1;
-    int64_t blocks = (int64_t)per_sm * P->sm_count;
-    const int64_t need = fem_div_up(P->n_slices, NPAIR);
-    if (blocks > need) blocks = need;
-    kern<<<(unsigned)blocks, 64 * NPAIR, smem, st>>>(A, M);
-  } else if (g_fem_tuning.assemble_variant == 7 || (g_fem_tuning.assemble_variant == 0 && MODE == MODE_ELASTIC)) {  // one slice per warp
+  if (g_fem_tuning.assemble_variant == 7 || (g_fem_tuning.assemble_variant == 0 && MODE == MODE_ELASTIC)) {  // one slice per warp
     auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A, M);
@@ -1049,21 +808,16 @@ static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   const int variant = g_fem_tuning.assemble_variant;
   // measured defaults (tools/tune.py, 16M elements): elastic -> one-shot TMA, tangent(+force) -> persistent pipelined TMA,
   // reference-order tangent (reads K_elast in its write-out) -> register kernel
-  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && MODE != MODE_TANGENT_REF) || (variant >= 6 && variant <= 9))) {
+  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && MODE != MODE_TANGENT_REF) || (variant == 6 || variant == 7))) {
     const int rc = launch_assemble_tma<MODE == MODE_FORCE_ONLY ? MODE_TANGENT : MODE, FORCE>(P, A, st);
     if (rc >= 0) return rc;  // -1: inputs not 16-byte aligned / too much shared memory -> register kernel
   }
   if (MODE != MODE_FORCE_ONLY && variant != 1) {
     const unsigned blocks = (unsigned)fem_div_up(P->n_slices * 32, 128);
     bool done = true;
-    if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 8) {
-      // launch-shape variants of the P1 kernel (tuning knob assemble_variant: 2 = default unpipelined, 3/4 = data double-buffered with 2/3 blocks per SM)
-      if (variant == 3) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, true, 2><<<blocks, 128, 0, st>>>(A);
-      else if (variant == 4) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, true, 3><<<blocks, 128, 0, st>>>(A);
-      else assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8, false, 1><<<blocks, 128, 0, st>>>(A);  // measured best (tools/tune.py)
-    }
-    else if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 12) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 12, false, 1><<<blocks, 128, 0, st>>>(A);
-    else if (P->n_p == 4 && P->n_q == 4 && P->max_degree <= 12) assemble_rows_reg_kernel<4, 4, MODE, FORCE, 12, false, 2><<<blocks, 128, 0, st>>>(A);
+    if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 8) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 8><<<blocks, 128, 0, st>>>(A);
+    else if (P->n_p == 3 && P->n_q == 1 && P->max_degree <= 12) assemble_rows_reg_kernel<3, 1, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
+    else if (P->n_p == 4 && P->n_q == 4 && P->max_degree <= 12) assemble_rows_reg_kernel<4, 4, MODE, FORCE, 12><<<blocks, 128, 0, st>>>(A);
     else done = false;
     if (done) {
       FEM_CUDA_CHECK(cudaGetLastError());

@@ -25,7 +25,7 @@ struct FemTuning {
   int assemble_warps;      // warps per block of the assembly kernel (0 = 4)
   int spmv_group;          // lanes per node in the SpMV (0 = by degree)
   int spmv_blocks_per_sm;  // 0 = 32
-  int assemble_variant;    // 0 auto, 1 shared-memory accumulators, 2 register accumulators when possible
+  int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D)
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
 };
 extern FemTuning g_fem_tuning;
