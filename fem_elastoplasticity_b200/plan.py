@@ -62,6 +62,7 @@ class FemPlan:
             raise ValueError("elements must be (n_p, n_e) and coordinates (2, n_n)")
         self.n_p, self.n_e = int(el.shape[0]), int(el.shape[1])
         self.n_n = int(co.shape[1])
+        self.coord = co                                   # (2, n_n) device coordinates (two-level preconditioner)
         d1 = np.ascontiguousarray(np.asarray(dhatp1, dtype=np.float64).reshape(self.n_p, -1))
         d2 = np.ascontiguousarray(np.asarray(dhatp2, dtype=np.float64).reshape(self.n_p, -1))
         w = np.ascontiguousarray(np.asarray(wf, dtype=np.float64).ravel())

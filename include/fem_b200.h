@@ -149,6 +149,26 @@ int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const
 int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const uint8_t* free_mask, double rtol,
             int maxit, int check_every, double* x, double* work, int* h_iters, double* h_relres, fem_stream stream);
 
+/* ---- two-level additive preconditioner M^-1 = D^-1 + P A_c^-1 P^T (csrc/twolevel.cu) ---------------------------------
+ * P: bilinear interpolation from a coarse grid of ncx x ncy cells of size hx x hy with origin (x0, y0) laid over the mesh's
+ * bounding box to the fine nodes (coord = the (2, n_n) coordinates), Dirichlet rows zeroed; n_c = 2 (ncx+1)(ncy+1).
+ * fem_coarse_galerkin: Ac[n_c][n_c] = P^T K P (zero-filled by the call, accumulated with FP64 atomics; once per matrix).
+ * fem_dense_gemv: y = A x, dense row-major (applies the inverted coarse operator).
+ * fem_tl_init: r = mask (rhs - Kx0) (Kx0 nullable), rc = P^T r, scal[1] = r'r, scal[4] = |rhs|^2 (scal and rc zeroed first).
+ * fem_tl_update_xr: x += alpha p, r -= alpha q, scal[1] += r'r, rc = P^T r (alpha from scal as in fem_pcg_update_xr).
+ * fem_tl_apply: z = minv r + P zc;  mode 0: scal[slot] += r'z;  mode 1: p = z;  mode 2: p = z + beta p (beta from scal).
+ * Together with fem_pcg_spmv_dot these are the steps of the preconditioned CG; the host sequences them.                  */
+int fem_coarse_galerkin(const fem_plan* plan, const double* K_vals, const uint8_t* free_mask, const double* coord, double x0,
+                        double y0, double hx, double hy, int ncx, int ncy, double* Ac, fem_stream stream);
+int fem_dense_gemv(int n, const double* A, const double* x, double* y, fem_stream stream);
+int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* coord, double x0,
+                double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal, fem_stream stream);
+int fem_tl_update_xr(int64_t n_n, const double* p, const double* q, const double* coord, double x0, double y0, double hx, double hy,
+                     int ncx, int ncy, double* x, double* r, double* rc, double* scal, int iter, fem_stream stream);
+int fem_tl_apply(int64_t n_n, int mode, const double* r, const double* minv, const uint8_t* free_mask, const double* coord, double x0,
+                 double y0, double hx, double hy, int ncx, int ncy, const double* zc, double* p, double* scal, int slot, int iter,
+                 fem_stream stream);
+
 /* energy products for the Newton stopping criterion: out[i] = v_i' K v_i, i < 3 (device double[3], overwritten) */
 int fem_energy_norms(const fem_plan* plan, const double* K_vals, const double* v0, const double* v1, const double* v2,
                      double* work, double* out, fem_stream stream);

@@ -466,3 +466,40 @@ def test_tsx_p2_unstructured(fem, golden):
     E = P.strain(u).cpu().numpy()
     for row, val in zip(E, (1e-3, 5e-4, -2e-3 + 4e-3)):
         assert np.abs(row - val).max() <= 1e-11
+
+
+def test_two_level_pcg(fem, golden):
+    """Two-level preconditioned CG (Jacobi + coarse-grid correction): same solution as the dense solve, far fewer iterations."""
+    from fem_elastoplasticity_b200 import meshgen
+    from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+    torch = fem["torch"]
+    d1, d2, wf = tables(fo.ElementType.P1)
+    # (a) unstructured tsx mesh (domain with a hole: some coarse nodes have no support) against the dense solve
+    g = golden("assembly_tsx_p1.npz")
+    n_e = g["elements"].shape[1]
+    P = fem["plan"].FemPlan(g["elements"], g["coordinates"], d1, d2, wf)
+    vals = P.assemble_elastic(float(g["shear"]) * np.ones(n_e), float(g["bulk"]) * np.ones(n_e))
+    q = fo.tsx_q_mask(g["coordinates"])
+    mask = P.mask_u8(q)
+    rhs = np.random.default_rng(5).standard_normal(P.n_dof)
+    tl = TwoLevelPCG(P, mask, nc=6)
+    x, its, rel = tl.solve(vals, P._f64(rhs), rtol=1e-13, maxit=5000, check_every=5)
+    ref = fo.masked_dense_solve(csr_from(g, "K", shape=(P.n_dof, P.n_dof)), rhs, q)
+    assert rel <= 1e-13
+    np.testing.assert_allclose(x.cpu().numpy(), ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+    _, its_j, _ = P.pcg(vals, rhs, mask, rtol=1e-13, maxit=20000, check_every=5)
+    assert its < its_j
+    # (b) footing problem, 160 x 160 cells: the CPU prototype needs 3551 Jacobi / 430 two-level iterations (H/h = 10)
+    m = meshgen.square_mesh_p1(160, 160)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    G, Kb, _, _ = meshgen.footing_materials(P.n_int)
+    k = P.assemble_elastic(G, Kb)
+    mask = P.mask_u8(m["Q"])
+    ud = (-1e-3 * m["dirichlet_nodes"]).t().reshape(-1).contiguous()
+    f = -P.spmv(k, ud)
+    xj, its_j, _ = P.pcg(k, f, mask, rtol=1e-10, maxit=20000, check_every=25)
+    tl = TwoLevelPCG(P, mask, nc=16)
+    xt, its_t, rel = tl.solve(k, f, rtol=1e-10, maxit=20000, check_every=5)
+    print("jacobi", its_j, "two-level", its_t)
+    assert 3000 < its_j < 4200 and 300 < its_t < 600
+    assert float((xt - xj).abs().max() / xj.abs().max()) < 1e-6
