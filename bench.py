@@ -263,6 +263,21 @@ def run_gpu(args):
         return b0.elapsed_time(b1) / reps
     t_tan_only = iso(lambda: P.assemble_tangent(rm["ds"], out=k_tan))
     t_el_only = iso(lambda: P.assemble_elastic(G, Kb, out=k_el))
+    # ---- one CONVERGED inner solve (rtol 1e-10) of the step's system with the two-level preconditioner (single rank)
+    conv = None
+    if world == 1 and not args.no_converged_solve:
+        from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+        tl = TwoLevelPCG(P, mask, nc=args.coarse_cells).setup(k_el)
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        _, c_its, c_rel = tl.solve(k_tan, rhs, rtol=1e-10, maxit=50000, check_every=50)
+        torch.cuda.synchronize()
+        c_s = time.perf_counter() - c0
+        conv = {"preconditioner": f"two-level: Jacobi + {tl.grid[4]}x{tl.grid[5]} bilinear coarse grid ({tl.ncd} coarse DOFs, dense inverse)",
+                "rtol": 1e-10, "iterations": c_its, "relres": c_rel, "seconds": c_s, "ms_per_iteration": 1e3 * c_s / max(c_its, 1),
+                "coarse_setup_seconds": tl.setup_seconds,
+                "jacobi_reference": "57 500 iterations / 41.7 s for the footing's elastic solve on this mesh (tools/full_solve.py)"}
+        del tl
     # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned); every step uploads its DS
     # (H2D) and downloads its K values (D2H) inside the timed region.  Two steps are in flight on two streams with
     # double-buffered device arrays, so the upload of step i+1 overlaps the download of step i (PCIe is full duplex).
@@ -349,6 +364,7 @@ def run_gpu(args):
                   "assembly_ms": t_asm, "return_map_ms": t_rm, "tangent_only_isolated_ms": t_tan_only,
                   "tangent_only_isolated_melem_s": n_e_tot / (t_tan_only * 1e-3) / 1e6,
                   "elastic_isolated_melem_s": n_e_tot / (t_el_only * 1e-3) / 1e6, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
+        "pcg_converged_solve": conv,
         "roofline": roof, "rooflines": rooflines, "clocks": clocks,
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent: pinned host DS -> device -> kernel -> pinned host K values, every step; two steps in flight "
@@ -380,6 +396,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: nx x nx cells per GPU (config 5 at 8 GPUs); strong: one nx x nx mesh split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-converged-solve", action="store_true", help="skip the converged two-level PCG solve reported beside the fixed-iteration step")
+    ap.add_argument("--coarse-cells", type=int, default=64)
     ap.add_argument("--halo", default="nccl", choices=["auto", "nccl", "peer"], help="multi-GPU halo exchange of the PCG")
     ap.add_argument("--no-graph", action="store_true", help="launch the PCG iterations eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -16,7 +16,7 @@ from .plan import FemPlan, axpby, dp_return_map
 
 class NewtonSolver:
     def __init__(self, plan: FemPlan, shear, bulk, eta, c, q_mask, pcg_rtol=1e-13, pcg_maxit=200000, check_every=50,
-                 tangent_mode="direct"):
+                 tangent_mode="direct", precond="jacobi", coarse_cells=64):
         self.plan = plan
         dev = plan.device
         f = plan._f64
@@ -25,6 +25,7 @@ class NewtonSolver:
         self.mask = plan.mask_u8(q_mask)
         self.pcg_rtol, self.pcg_maxit, self.check_every = pcg_rtol, pcg_maxit, check_every
         self.tangent_mode = tangent_mode
+        self.precond, self.coarse_cells, self._tl = precond, coarse_cells, None   # "jacobi" | "twolevel" (see twolevel.py)
         self.k_elast = plan.assemble_elastic(self.shear, self.bulk)
         self.k_tan = plan.empty(plan.nnz)
         self.E = plan.empty(3, plan.n_int)
@@ -43,6 +44,12 @@ class NewtonSolver:
                              want_ep=False, out=self.rm)
 
     def solve(self, k_vals, rhs, x0=None):
+        if self.precond == "twolevel":
+            if self._tl is None:                          # coarse operator of K_elast, kept for every tangent solve
+                from .twolevel import TwoLevelPCG
+                self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells).setup(self.k_elast)
+            x, its, rel = self._tl.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=min(self.check_every, 10))
+            return x.clone(), its, rel
         return self.plan.pcg(k_vals, rhs, self.mask, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every,
                              x0=x0, work=self.work)
 
@@ -69,7 +76,8 @@ class NewtonSolver:
         return u_new, crit, n_plast, its
 
 
-def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, tangent_mode="direct", log=None):
+def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi",
+                   coarse_cells=64):
     """Strip-footing load stepping of Plasticity2D_DP.elasticity_fem (:986-1131) on the device.
     ``mesh``: dict with coordinates (2,n_n), elements (3,n_e), Q, dirichlet_nodes (NumPy or CUDA tensors)."""
     from . import pythonFEM as api
@@ -81,7 +89,7 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
     dev = P.device
     G, Kb, eta, c = footing_materials(P.n_int, dev)
     c0 = 450
-    ns = NewtonSolver(P, G, Kb, eta, c, mesh["Q"], pcg_rtol=pcg_rtol, tangent_mode=tangent_mode)
+    ns = NewtonSolver(P, G, Kb, eta, c, mesh["Q"], pcg_rtol=pcg_rtol, tangent_mode=tangent_mode, precond=precond, coarse_cells=coarse_cells)
     dn = torch.as_tensor(np.asarray(mesh["dirichlet_nodes"].cpu() if isinstance(mesh["dirichlet_nodes"], torch.Tensor)
                                     else mesh["dirichlet_nodes"], dtype=np.float64)).to(dev)
     q_nd = dn[1] > 0
@@ -134,7 +142,7 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
             "Ep": ep_old.cpu().numpy()}
 
 
-def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None):
+def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi", coarse_cells=8):
     """tsx-tunnel load stepping (tsx-tunnel/pythonFEM.py:1661-1830) for P1 on the device."""
     from . import pythonFEM as api
     et = api.LagrangeElementType.P1
@@ -158,7 +166,8 @@ def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct
     P = FemPlan(elem, coords, d1, d2, wf)
     n_int = P.n_int
     ones = np.ones(n_int)
-    ns = NewtonSolver(P, shear0 * ones, bulk0 * ones, eta0 * ones, c0 * ones, q, pcg_rtol=pcg_rtol, tangent_mode=tangent_mode)
+    ns = NewtonSolver(P, shear0 * ones, bulk0 * ones, eta0 * ones, c0 * ones, q, pcg_rtol=pcg_rtol, tangent_mode=tangent_mode,
+                      precond=precond, coarse_cells=coarse_cells)
     s_init = torch.as_tensor(np.tile(s0.reshape(-1, 1), (1, n_int))).to(P.device)
     f0 = P.internal_force(s_init)                                     # :1737
     rhs = axpby(-1.0, f0, 0.0, f0)

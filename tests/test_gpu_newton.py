@@ -61,3 +61,22 @@ def test_tangent_reference_mode_driver(golden):
     b = newton.tsx_driver(m["coordinates"], m["elements"], tangent_mode="direct")
     assert a["steps"] == b["steps"] == 17
     assert np.abs(a["U"] - b["U"]).max() <= 1e-10 * np.abs(a["U"]).max()
+
+
+def test_drivers_with_two_level_preconditioner(golden):
+    """Whole load-stepping runs with the two-level PCG as the inner solver: same Newton traces and displacements."""
+    from fem_elastoplasticity_b200 import newton
+    m = golden("assembly_tsx_p1.npz")
+    a = newton.tsx_driver(m["coordinates"], m["elements"], precond="twolevel", coarse_cells=8)
+    oref = fo.tsx_driver(m["coordinates"], m["elements"])
+    assert a["steps"] == oref["steps"] == 17
+    assert [t[1:3] for t in a["trace"]] == [t[1:3] for t in oref["trace"]]
+    assert np.abs(a["U"] - oref["U"]).max() <= 1e-10 * np.abs(oref["U"]).max()
+    f = golden("assembly_footing_p1_l1.npz")
+    mesh = {k: f[k] for k in ("coordinates", "elements", "Q", "dirichlet_nodes")}
+    b = newton.footing_driver(mesh, precond="twolevel", coarse_cells=4)
+    g = golden("footing_l1_trace.npz")
+    crit = np.array([t[3] for t in b["trace"]])
+    assert crit.shape == (109,)
+    np.testing.assert_allclose(crit, g["criterion"], rtol=1e-5, atol=1e-12)
+    assert sum(t[4] for t in b["trace"]) < 0.7 * 109 * 300          # far fewer inner iterations than Jacobi (~300-400 each)
