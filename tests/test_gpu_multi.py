@@ -47,6 +47,10 @@ def _worker(rank, world, port, nx, ny, out_dir):
         res[name] = x.cpu().numpy().copy()
         res[name + "_its"] = its
         res[name + "_is_peer"] = pcg.peer is not None
+    from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+    tl = TwoLevelPCG(P, mask, nc=8, part=part)
+    x, its, rel = tl.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=5)
+    res["twolevel"], res["twolevel_its"], res["twolevel_is_peer"] = x.cpu().numpy().copy(), its, False
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, own=np.array(part.owned_dof_range()), **res)
     dist.destroy_process_group()
 
@@ -71,7 +75,7 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
     b = np.random.default_rng(9).standard_normal(P.n_dof)
     ref, its, rel = P.pcg(k, b, P.mask_u8(m["Q"]), rtol=1e-12, maxit=20000, check_every=25)
     ref = ref.cpu().numpy()
-    for name in ("nccl", "peer"):
+    for name in ("nccl", "peer", "twolevel"):
         got = np.full_like(ref, np.nan)
         for r in range(world):
             d = np.load(tmp_path / f"r{r}.npz")
@@ -82,6 +86,7 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
                 assert bool(d["peer_is_peer"]), "symmetric-memory halo was not active"
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+    assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 3
 
 
 def test_single_rank_graph_pcg_matches_c_loop():
