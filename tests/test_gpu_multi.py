@@ -86,7 +86,7 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
                 assert bool(d["peer_is_peer"]), "symmetric-memory halo was not active"
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
-    assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 3
+    assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 2   # H/h = 24 here
 
 
 def test_single_rank_graph_pcg_matches_c_loop():
