@@ -888,6 +888,7 @@ static void fill_args(const fem_plan* P, AsmArgs& A) {
 extern "C" int fem_assemble_elastic(const fem_plan* P, const double* shear, const double* bulk, double* K_vals,
                                     fem_stream stream) {
   FEM_REQUIRE(P && shear && bulk && K_vals, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0, "K_vals must be 16-byte aligned");
   AsmArgs A;
   fill_args(P, A);
   A.shear = shear; A.bulk = bulk; A.K_vals = K_vals;
@@ -896,6 +897,7 @@ extern "C" int fem_assemble_elastic(const fem_plan* P, const double* shear, cons
 
 extern "C" int fem_assemble_tangent(const fem_plan* P, const double* DS, double* K_vals, fem_stream stream) {
   FEM_REQUIRE(P && DS && K_vals, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0, "K_vals must be 16-byte aligned");
   AsmArgs A;
   fill_args(P, A);
   A.DS = DS; A.K_vals = K_vals;
@@ -905,6 +907,7 @@ extern "C" int fem_assemble_tangent(const fem_plan* P, const double* DS, double*
 extern "C" int fem_assemble_tangent_ref(const fem_plan* P, const double* DS, const double* shear, const double* bulk,
                                         const double* K_elast_vals, double* K_vals, fem_stream stream) {
   FEM_REQUIRE(P && DS && shear && bulk && K_elast_vals && K_vals, "null pointer");
+  FEM_REQUIRE(((reinterpret_cast<uintptr_t>(K_vals) | reinterpret_cast<uintptr_t>(K_elast_vals)) & 15u) == 0, "K_vals and K_elast_vals must be 16-byte aligned");
   AsmArgs A;
   fill_args(P, A);
   A.DS = DS; A.shear = shear; A.bulk = bulk; A.Kel = K_elast_vals; A.K_vals = K_vals;
@@ -914,7 +917,7 @@ extern "C" int fem_assemble_tangent_ref(const fem_plan* P, const double* DS, con
 extern "C" int fem_assemble_tangent_force(const fem_plan* P, const double* DS, const double* S, double* K_vals, double* F,
                                           fem_stream stream) {
   FEM_REQUIRE(P && DS && S && K_vals && F, "null pointer");
-  FEM_REQUIRE((reinterpret_cast<uintptr_t>(F) & 15u) == 0, "F must be 16-byte aligned");
+  FEM_REQUIRE(((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(K_vals)) & 15u) == 0, "F and K_vals must be 16-byte aligned");
   AsmArgs A;
   fill_args(P, A);
   A.DS = DS; A.S = S; A.K_vals = K_vals; A.F = F;
