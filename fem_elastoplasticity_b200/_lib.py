@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfem_b200.so")
+LIB_PATH = os.environ.get("FEM_B200_LIB") or os.path.join(_HERE, "libfem_b200.so")   # override: A/B builds of the kernels
 
 STATUS = {0: "FEM_OK", 1: "FEM_ERR_INVALID_ARG", 2: "FEM_ERR_CUDA", 3: "FEM_ERR_NONFINITE_JACOBIAN",
           4: "FEM_ERR_PCG_BREAKDOWN", 5: "FEM_ERR_PCG_MAXIT", 6: "FEM_ERR_UNSUPPORTED", 7: "FEM_ERR_NO_DEVICE"}

@@ -318,8 +318,7 @@ struct StageLayout {
   __host__ __device__ static constexpr int t2_b(int w) { return MODE == MODE_TANGENT_REF ? pad128(w * 8) : 0; }
   __host__ __device__ static constexpr int s_b(int w) { return FORCE ? pad128(3 * w * 8) : 0; }
   __host__ __device__ static constexpr int box_b(int w) { return geom_b(w) + t0_b(w) + t1_b(w) + t2_b(w) + s_b(w); }
-  // two boxes + mbarriers (128 B) + two 8 x 32 buffers of incidence words (variant D)
-  __host__ __device__ static constexpr int warp_b(int w) { return 2 * box_b(w) + 128 + 2048; }
+  __host__ __device__ static constexpr int warp_b(int w) { return 2 * box_b(w) + 128; }  // + mbarrier
 };
 
 __device__ __forceinline__ void tma_box_2d(uint32_t dst, const CUtensorMap* map, int c0, uint32_t bar) {
@@ -571,30 +570,11 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
     if (s < n_slices) { k.sbase = A.slice_ptr[s]; k.width = (int)((A.slice_ptr[s + 1] - k.sbase) >> 5); }
   };
   Book cur, nxt;
-  // Incidence words live in shared memory ([i][lane], two buffers: current and next slice) instead of a rotating register
-  // queue.  A node's words are ordered box 0 first, so pass 0 only walks [0, max n0) and pass 1 [min n0, width) - warp-uniform
-  // bounds, n0 = number of this lane's incidences whose element is in box 0.
-  uint32_t* wbuf = reinterpret_cast<uint32_t*>(wbase + 2 * L::box_b(bw) + 128);
-  uint32_t nwords[CH];
-  int cbuf = 0;
-  auto stash = [&](int buf, const uint32_t (&w)[CH], int width, bool staged_, int& n0_min, int& n0_max) {
-    int n0 = 0;
-#pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (i < width) {
-        wbuf[(buf * CH + i) * 32 + lane] = w[i];
-        n0 += ((w[i] & 0x80000000u) && (!staged_ || (int)(w[i] & 0x1FF) < bw)) ? 1 : 0;
-      }
-    n0_min = __reduce_min_sync(0xffffffffu, n0);
-    n0_max = __reduce_max_sync(0xffffffffu, n0);
-  };
+  uint32_t words[CH], nwords[CH];
   load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
   load_sell(slice1, nxt);
 #pragma unroll
-  for (int i = 0; i < CH; ++i) nwords[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
-  int n0_min = 0, n0_max = 0;
-  stash(0, nwords, cur.width, cur.nb >= 1 && cur.nb <= 2, n0_min, n0_max);
-  __syncwarp();
+  for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
   if (slice < n_slices && lane == 0 && cur.nb >= 1 && cur.nb <= 2) {
     issue_box<MODE, FORCE>(M, box0, bw, cur.st0, bar0);
     if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
@@ -612,7 +592,6 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
     const int nb = cur.nb;
     const bool staged = nb >= 1 && nb <= 2;
     const int64_t a = slice * 32 + lane;
-    const uint32_t* wcur = wbuf + cbuf * CH * 32 + lane;
     double acc[MAXDEG][4];
 #pragma unroll
     for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
@@ -626,10 +605,12 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
         else if (nb == 2) { mbar_wait(bar1, ph1); ph1 ^= 1; }
       }
       if (pass == 0 || (staged && nb == 2)) {
-        const int i_lo = pass ? n0_min : 0, i_hi = pass ? cur.width : n0_max;
 #pragma unroll 1
-        for (int i = i_lo; i < i_hi; ++i) {
-          const uint32_t word = wcur[i * 32];
+        for (int i = 0; i < CH; ++i) {  // rotate the whole queue so that it is back in place for the next pass
+          const uint32_t word = words[0];
+#pragma unroll
+          for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
+          words[CH - 1] = word;
           if (!(word & 0x80000000u)) continue;
           const int li = word & 0x1FF;
           if (staged && ((li >= bw) != (pass == 1))) continue;
@@ -663,7 +644,7 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
 #pragma unroll
               for (int k = 0; k < 3; ++k) pd.s[k] = sp[k * bw];
             }
-          } else {  // direct loads (slices with more than two boxes): entry i is incidence i
+          } else {  // direct loads (slices with more than two boxes); i-th entry of the queue is incidence i
             const uint32_t key = A.inc_key[cur.sbase + (int64_t)i * 32 + lane];
             load_point<NP, MODE, FORCE>(A, (int64_t)(key >> 3), pd);
           }
@@ -721,9 +702,8 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
     cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
     cur.sbase = nxt.sbase; cur.width = nxt.width;
     nxt.sbase = nn.sbase; nxt.width = nn.width;
-    cbuf ^= 1;
-    stash(cbuf, nwords, cur.width, cur.nb >= 1 && cur.nb <= 2, n0_min, n0_max);   // the other buffer: nobody reads it any more
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CH; ++i) words[i] = nwords[i];
   }
 }
 
