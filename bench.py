@@ -365,6 +365,7 @@ def run_gpu(args):
                   "tangent_only_isolated_melem_s": n_e_tot / (t_tan_only * 1e-3) / 1e6,
                   "elastic_isolated_melem_s": n_e_tot / (t_el_only * 1e-3) / 1e6, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
         "pcg_converged_solve": conv,
+        "newton_step_converged_s": (None if conv is None else (t_strain + t_rm + t_asm + t_crit) * 1e-3 + conv["seconds"]),
         "roofline": roof, "rooflines": rooflines, "clocks": clocks,
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent: pinned host DS -> device -> kernel -> pinned host K values, every step; two steps in flight "
