@@ -54,9 +54,9 @@ SIGNATURES = {
     "fem_pcg_update_p_push": [_i64, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i64, _i64, _vp, _vp],
     "fem_pcg": [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl), _vp],
     "fem_coarse_galerkin": [_vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp],
-    "fem_dense_gemv": [_i32, _vp, _vp, _vp, _vp],
-    "fem_tl_init": [_i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp],
-    "fem_tl_update_xr": [_i64, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
+    "fem_dense_gemv": [_i32, _vp, _vp, _vp, _vp, _vp],
+    "fem_tl_init": [_i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp],
+    "fem_tl_update_xr": [_i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
     "fem_tl_apply": [_i64, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
     "fem_energy_norms": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fem_vec_axpby": [_i64, _dbl, _vp, _dbl, _vp, _vp, _vp],

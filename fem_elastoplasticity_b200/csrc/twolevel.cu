@@ -121,10 +121,10 @@ __device__ __forceinline__ int rz_new_slot2(int it) { return (it & 1) ? 0 : 2; }
 
 // r = mask (b - K x0);  r_c += P^T r;  |b|^2, r'r
 __global__ void __launch_bounds__(256) tl_init_kernel(int64_t n_n, CoarseGrid g, const double2* __restrict__ rhs, const double2* __restrict__ Kx0,
-                                                      const uint8_t* __restrict__ mask, const double* __restrict__ coord, double2* __restrict__ r,
-                                                      double* rc, double* scal) {
+                                                      const uint8_t* __restrict__ mask, const double2* __restrict__ minv,
+                                                      const double* __restrict__ coord, double2* __restrict__ r, double* rc, double* scal) {
   __shared__ double red[32];
-  double rr = 0.0, bb = 0.0;
+  double rr = 0.0, bb = 0.0, rdr = 0.0;
   const int64_t n_pad = (n_n + 31) & ~(int64_t)31;
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_pad; a += (int64_t)gridDim.x * blockDim.x) {
     const bool valid = a < n_n;
@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(256) tl_init_kernel(int64_t n_n, CoarseGrid g,
       r[a] = ri;
       rr = fma(ri.x, ri.x, fma(ri.y, ri.y, rr));
       bb = fma(b.x, b.x, fma(b.y, b.y, bb));
+      const double2 mi = minv[a];
+      rdr = fma(ri.x * mi.x, ri.x, fma(ri.y * mi.y, ri.y, rdr));
       x = coord[a];
       y = coord[n_n + a];
     }
@@ -151,20 +153,23 @@ __global__ void __launch_bounds__(256) tl_init_kernel(int64_t n_n, CoarseGrid g,
   }
   rr = block_sum(rr, red);
   bb = block_sum(bb, red);
+  rdr = block_sum(rdr, red);
   if (threadIdx.x == 0) {
     atomicAdd(scal + 1, rr);
     atomicAdd(scal + 4, bb);
+    atomicAdd(scal + 0, rdr);
   }
 }
 
-// x += alpha p; r -= alpha q; r'r; r_c += P^T r
+// x += alpha p; r -= alpha q; r'r; r_c += P^T r; and the Jacobi part of r'z:  r'z = r'D^-1 r + r'(P z_c), where
+// r'(P z_c) = (P^T r)'z_c = r_c'z_c is added by the coarse GEMV - no separate pass over the vectors for r'z.
 __global__ void __launch_bounds__(256) tl_update_xr_kernel(int64_t n_n, CoarseGrid g, const double2* __restrict__ p, const double2* __restrict__ q,
-                                                           const double* __restrict__ coord, double2* __restrict__ x, double2* __restrict__ r,
-                                                           double* rc, double* scal, int it) {
+                                                           const double2* __restrict__ minv, const double* __restrict__ coord,
+                                                           double2* __restrict__ x, double2* __restrict__ r, double* rc, double* scal, int it) {
   __shared__ double red[32];
   const double rz_old = scal[rz_old_slot2(it)], pq = scal[3];
   const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
-  double rr = 0.0;
+  double rr = 0.0, rdr = 0.0;
   const int64_t n_pad = (n_n + 31) & ~(int64_t)31;
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_pad; a += (int64_t)gridDim.x * blockDim.x) {
     const bool valid = a < n_n;
@@ -181,13 +186,19 @@ __global__ void __launch_bounds__(256) tl_update_xr_kernel(int64_t n_n, CoarseGr
       x[a] = xi;
       r[a] = ri;
       rr = fma(ri.x, ri.x, fma(ri.y, ri.y, rr));
+      const double2 mi = minv[a];
+      rdr = fma(ri.x * mi.x, ri.x, fma(ri.y * mi.y, ri.y, rdr));
       cx = coord[a];
       cy = coord[n_n + a];
     }
     restrict_warp(g, valid, cx, cy, ri.x, ri.y, rc);
   }
   rr = block_sum(rr, red);
-  if (threadIdx.x == 0) atomicAdd(scal + 1, rr);
+  rdr = block_sum(rdr, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(scal + 1, rr);
+    atomicAdd(scal + rz_new_slot2(it), rdr);
+  }
 }
 
 // z = minv r + P z_c;  MODE 0: r'z into scal[slot];  MODE 1: p = z (first direction);  MODE 2: p = z + beta p
@@ -231,7 +242,8 @@ __global__ void __launch_bounds__(256) tl_z_kernel(int64_t n_n, CoarseGrid g, co
 }
 
 // y = A x, dense row-major n x n (the inverted coarse operator): one warp per row, coalesced double2 loads
-__global__ void __launch_bounds__(256) dense_gemv_kernel(int n, const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y) {
+__global__ void __launch_bounds__(256) dense_gemv_kernel(int n, const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y,
+                                                         double* dot) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const double* row = A + (int64_t)warp * n;
@@ -247,7 +259,10 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(int n, const double* __
     for (int j = lane; j < n; j += 32) acc = fma(__ldcs(row + j), x[j], acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) y[warp] = acc;
+  if (lane == 0) {
+    y[warp] = acc;
+    if (dot) atomicAdd(dot, x[warp] * acc);  // x'Ax: the coarse part r_c'z_c of r'z
+  }
 }
 
 static unsigned tl_grid(int64_t n) {
@@ -278,36 +293,39 @@ extern "C" int fem_coarse_galerkin(const fem_plan* P, const double* K_vals, cons
   return FEM_OK;
 }
 
-extern "C" int fem_dense_gemv(int n, const double* A, const double* x, double* y, fem_stream stream) {
+extern "C" int fem_dense_gemv(int n, const double* A, const double* x, double* y, double* dot, fem_stream stream) {
   FEM_REQUIRE(n > 0 && A && x && y, "null pointer");
-  dense_gemv_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, A, x, y);
+  dense_gemv_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, A, x, y, dot);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
 
-extern "C" int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* coord, double x0,
-                           double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal, fem_stream stream) {
-  FEM_REQUIRE(rhs && coord && r && rc && scal && n_n > 0, "null pointer");
+extern "C" int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv, const double* coord,
+                           double x0, double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal,
+                           fem_stream stream) {
+  FEM_REQUIRE(rhs && minv && coord && r && rc && scal && n_n > 0, "null pointer");
   CoarseGrid g;
   if (int rcode = make_grid(g, x0, y0, hx, hy, ncx, ncy)) return rcode;
   cudaStream_t st = (cudaStream_t)stream;
   FEM_CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
   FEM_CUDA_CHECK(cudaMemsetAsync(rc, 0, sizeof(double) * 2 * (ncx + 1) * (ncy + 1), st));
   tl_init_kernel<<<tl_grid(n_n), 256, 0, st>>>(n_n, g, reinterpret_cast<const double2*>(rhs), reinterpret_cast<const double2*>(Kx0), free_mask,
-                                               coord, reinterpret_cast<double2*>(r), rc, scal);
+                                               reinterpret_cast<const double2*>(minv), coord, reinterpret_cast<double2*>(r), rc, scal);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
 
-extern "C" int fem_tl_update_xr(int64_t n_n, const double* p, const double* q, const double* coord, double x0, double y0, double hx,
-                                double hy, int ncx, int ncy, double* x, double* r, double* rc, double* scal, int iter, fem_stream stream) {
-  FEM_REQUIRE(p && q && coord && x && r && rc && scal && n_n > 0, "null pointer");
+extern "C" int fem_tl_update_xr(int64_t n_n, const double* p, const double* q, const double* minv, const double* coord, double x0, double y0,
+                                double hx, double hy, int ncx, int ncy, double* x, double* r, double* rc, double* scal, int iter,
+                                fem_stream stream) {
+  FEM_REQUIRE(p && q && minv && coord && x && r && rc && scal && n_n > 0, "null pointer");
   CoarseGrid g;
   if (int rcode = make_grid(g, x0, y0, hx, hy, ncx, ncy)) return rcode;
   cudaStream_t st = (cudaStream_t)stream;
   FEM_CUDA_CHECK(cudaMemsetAsync(rc, 0, sizeof(double) * 2 * (ncx + 1) * (ncy + 1), st));
-  tl_update_xr_kernel<<<tl_grid(n_n), 256, 0, st>>>(n_n, g, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q), coord,
-                                                    reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), rc, scal, iter);
+  tl_update_xr_kernel<<<tl_grid(n_n), 256, 0, st>>>(n_n, g, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q),
+                                                    reinterpret_cast<const double2*>(minv), coord, reinterpret_cast<double2*>(x),
+                                                    reinterpret_cast<double2*>(r), rc, scal, iter);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

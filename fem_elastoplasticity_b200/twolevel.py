@@ -67,9 +67,12 @@ class TwoLevelPCG:
         self.setup_seconds = time.perf_counter() - t0
         return self
 
-    def _coarse_solve(self):
+    def _coarse_solve(self, rz_slot):
+        """z_c = A_c^-1 r_c (replicated on every rank) and the coarse part r_c'z_c of r'z (added once: by rank 0)."""
         self._reduce(self.rc)
-        call("fem_dense_gemv", self.ncd, _ptr(self.Aci), _ptr(self.rc), _ptr(self.zc), _stream())
+        lead = self.part is None or self.part.rank == 0
+        call("fem_dense_gemv", self.ncd, _ptr(self.Aci), _ptr(self.rc), _ptr(self.zc),
+             _ptr(self.scal[rz_slot:rz_slot + 1]) if lead else None, _stream())
 
     def solve(self, k_vals, rhs, rtol=1e-10, maxit=100000, check_every=25, iters=None):
         """Returns (x, iterations, relative residual).  ``iters``: run exactly that many iterations (benchmarks)."""
@@ -79,14 +82,12 @@ class TwoLevelPCG:
         n_n = P.n_n
         P.jacobi(k_vals, self.mask, out=self.minv)
         self.x.zero_()
-        call("fem_tl_init", n_n, _ptr(rhs), None, _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.r), _ptr(self.rc), _ptr(s), _stream())
-        self._reduce(s[0:5])
-        self._coarse_solve()
+        call("fem_tl_init", n_n, _ptr(rhs), None, _ptr(self.mask), _ptr(self.minv), _ptr(P.coord), *g, _ptr(self.r), _ptr(self.rc), _ptr(s),
+             _stream())
+        self._coarse_solve(0)                             # z_c, and r_c'z_c into s[0] (rank 0)
+        self._reduce(s[0:5])                              # r'z = sum r'D^-1 r + r_c'z_c, r'r, |b|^2
         call("fem_tl_apply", n_n, 1, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), _ptr(self.p),
              _ptr(s), 0, 0, _stream())
-        call("fem_tl_apply", n_n, 0, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), None, _ptr(s), 0, 0,
-             _stream())
-        self._reduce(s[0:1])
         n_it = iters if iters is not None else maxit
         it, rel = 0, float("inf")
         while it < n_it:
@@ -94,12 +95,9 @@ class TwoLevelPCG:
                 part.halo_exchange(self.p)
             call("fem_pcg_spmv_dot", P._h, _ptr(k_vals), _ptr(self.p), _ptr(self.q), _ptr(self.mask), _ptr(s), it, _stream())
             self._reduce(s[3:4])
-            call("fem_tl_update_xr", n_n, _ptr(self.p), _ptr(self.q), _ptr(P.coord), *g, _ptr(self.x), _ptr(self.r), _ptr(self.rc), _ptr(s),
-                 it, _stream())
-            self._coarse_solve()
-            new = 0 if it & 1 else 2
-            call("fem_tl_apply", n_n, 0, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), None, _ptr(s),
-                 new, it, _stream())
+            call("fem_tl_update_xr", n_n, _ptr(self.p), _ptr(self.q), _ptr(self.minv), _ptr(P.coord), *g, _ptr(self.x), _ptr(self.r),
+                 _ptr(self.rc), _ptr(s), it, _stream())
+            self._coarse_solve(0 if it & 1 else 2)        # + r_c'z_c into the r'z slot: no separate r'z pass
             self._reduce(s[1:3] if it % 2 == 0 else s[0:2])
             call("fem_tl_apply", n_n, 2, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), _ptr(self.p),
                  _ptr(s), 0, it, _stream())

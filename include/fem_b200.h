@@ -153,18 +153,21 @@ int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const
  * P: bilinear interpolation from a coarse grid of ncx x ncy cells of size hx x hy with origin (x0, y0) laid over the mesh's
  * bounding box to the fine nodes (coord = the (2, n_n) coordinates), Dirichlet rows zeroed; n_c = 2 (ncx+1)(ncy+1).
  * fem_coarse_galerkin: Ac[n_c][n_c] = P^T K P (zero-filled by the call, accumulated with FP64 atomics; once per matrix).
- * fem_dense_gemv: y = A x, dense row-major (applies the inverted coarse operator).
- * fem_tl_init: r = mask (rhs - Kx0) (Kx0 nullable), rc = P^T r, scal[1] = r'r, scal[4] = |rhs|^2 (scal and rc zeroed first).
- * fem_tl_update_xr: x += alpha p, r -= alpha q, scal[1] += r'r, rc = P^T r (alpha from scal as in fem_pcg_update_xr).
- * fem_tl_apply: z = minv r + P zc;  mode 0: scal[slot] += r'z;  mode 1: p = z;  mode 2: p = z + beta p (beta from scal).
+ * fem_dense_gemv: y = A x, dense row-major (applies the inverted coarse operator); if dot != NULL, *dot += x'y.
+ * r'z is never formed by a pass of its own: r'z = r'D^-1 r + r'(P z_c) and r'(P z_c) = (P^T r)'z_c = rc'zc, so
+ * fem_tl_init: r = mask (rhs - Kx0) (Kx0 nullable), rc = P^T r, scal[1] = r'r, scal[4] = |rhs|^2, scal[0] = r'D^-1 r
+ *   (scal and rc zeroed first);
+ * fem_tl_update_xr: x += alpha p, r -= alpha q, scal[1] += r'r, scal[rz_new] += r'D^-1 r, rc = P^T r (alpha from scal as in
+ *   fem_pcg_update_xr); the coarse GEMV then adds rc'zc to the same slot through its `dot` argument;
+ * fem_tl_apply: z = minv r + P zc;  mode 0: scal[slot] += r'z (checks);  mode 1: p = z;  mode 2: p = z + beta p.
  * Together with fem_pcg_spmv_dot these are the steps of the preconditioned CG; the host sequences them.                  */
 int fem_coarse_galerkin(const fem_plan* plan, const double* K_vals, const uint8_t* free_mask, const double* coord, double x0,
                         double y0, double hx, double hy, int ncx, int ncy, double* Ac, fem_stream stream);
-int fem_dense_gemv(int n, const double* A, const double* x, double* y, fem_stream stream);
-int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* coord, double x0,
-                double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal, fem_stream stream);
-int fem_tl_update_xr(int64_t n_n, const double* p, const double* q, const double* coord, double x0, double y0, double hx, double hy,
-                     int ncx, int ncy, double* x, double* r, double* rc, double* scal, int iter, fem_stream stream);
+int fem_dense_gemv(int n, const double* A, const double* x, double* y, double* dot, fem_stream stream);
+int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv, const double* coord,
+                double x0, double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal, fem_stream stream);
+int fem_tl_update_xr(int64_t n_n, const double* p, const double* q, const double* minv, const double* coord, double x0, double y0,
+                     double hx, double hy, int ncx, int ncy, double* x, double* r, double* rc, double* scal, int iter, fem_stream stream);
 int fem_tl_apply(int64_t n_n, int mode, const double* r, const double* minv, const uint8_t* free_mask, const double* coord, double x0,
                  double y0, double hx, double hy, int ncx, int ncy, const double* zc, double* p, double* scal, int slot, int iter,
                  fem_stream stream);
