@@ -149,7 +149,7 @@ def run_reference(args):
             "cpu_baseline": {"value": melem, "unit": "Melem/s", "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": melem, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,7 +198,7 @@ def run_gpu(args):
     rm = {}
     k_tan, F = P.empty(P.nnz), P.empty(P.n_dof)
     k_el = P.assemble_elastic(G, Kb)
-    pcg = fdist.DistributedPCG(P, part, mask, peer={"auto": "auto", "nccl": False, "peer": True}[args.halo], use_graph=not args.no_graph)
+    pcg = fdist.DistributedPCG(P, part, mask, peer={"auto": "auto", "nccl": False, "peer": True, "fused": "fused"}[args.halo], use_graph=not args.no_graph)
     rhs = P.empty(P.n_dof)
     from fem_elastoplasticity_b200.plan import axpby
 
@@ -355,8 +355,10 @@ def run_gpu(args):
         "config": {"workload": f"config {4 if (world == 1 or args.scaling == 'strong') else 5}: synthetic uniform P1 mesh {nx}x{ny_global} cells, {n_e_tot} elements "
                                f"({n_e_owned} per GPU, strip partition), DP return map + tangent assembly + PCG",
                    "n_elements": n_e_tot, "n_dof_per_gpu": n_dof_rank, "nnz_per_gpu": nnz_rank, "pcg_iters_per_step": args.pcg_iters,
-                   "preconditioner": "jacobi", "pcg_cuda_graph": bool(pcg.use_graph and pcg._graph is not None), "halo": ("nvlink peer stores fused into the p-update kernel (symmetric memory)" if pcg.peer is not None
-                                                         else ("none (1 GPU)" if world == 1 else "nccl send/recv")), "plastic_fraction": float(rm["ind_p"].double().mean().item()),
+                   "preconditioner": "jacobi", "pcg_cuda_graph": bool(pcg._graph is not None),
+                   "halo": ("fused iteration: halo + both reductions as nvlink peer stores/flags inside the 3 PCG kernels (symmetric memory)" if getattr(pcg, "fused", False)
+                            else "nvlink peer stores fused into the p-update kernel (symmetric memory), nccl all-reduces" if pcg.peer is not None
+                            else ("none (1 GPU)" if world == 1 else "nccl send/recv + all-reduces")), "plastic_fraction": float(rm["ind_p"].double().mean().item()),
                    "l2": "inputs larger than L2 (>=1 GB per array vs 126 MB), no flush needed",
                    "plan_build_s": t_plan, "plan_bytes": P.bytes},
         "parts": {"tangent_assembly_melem_s": n_e_tot / (t_asm * 1e-3) / 1e6, "return_map_mpts_s": n_int_tot / (t_rm * 1e-3) / 1e6,
@@ -380,12 +382,26 @@ def run_gpu(args):
                                           "the reference path is single-threaded",
                                 "return_map_mpts_s": r["n_e"] / r["t"]["return_map"] / 1e6,
                                 "pcg_ms_per_iter": 1e3 * r["t"]["pcg"] / max(args.pcg_iters, 1), "newton_step_s": r["t"]["step"]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = 1
+
+
+def emit(line):
+    """The ONE JSON line, on the real stdout (see main)."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner comes from C code, at
+    # the WARN level too) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -399,7 +415,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converged-solve", action="store_true", help="skip the converged two-level PCG solve reported beside the fixed-iteration step")
     ap.add_argument("--coarse-cells", type=int, default=64)
-    ap.add_argument("--halo", default="nccl", choices=["auto", "nccl", "peer"], help="multi-GPU halo exchange of the PCG")
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer", "fused"], help="multi-GPU exchanges of the PCG: fused = inside the kernels over NVLink peer memory; auto = fused, NCCL if symmetric memory is unavailable")
     ap.add_argument("--no-graph", action="store_true", help="launch the PCG iterations eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

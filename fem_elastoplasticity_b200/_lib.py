@@ -52,6 +52,11 @@ SIGNATURES = {
     "fem_pcg_update_p": [_i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "fem_halo_push": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp],
     "fem_pcg_update_p_push": [_i64, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _i64, _i64, _vp, _vp],
+    "fem_ppcg_words": [],
+    "fem_ppcg_begin": [_vp, _vp, _i32, _vp],
+    "fem_ppcg_spmv_dot": [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
+    "fem_ppcg_update_xr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
+    "fem_ppcg_update_p": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
     "fem_pcg": [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl), _vp],
     "fem_coarse_galerkin": [_vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp],
     "fem_dense_gemv": [_i32, _vp, _vp, _vp, _vp, _vp],

@@ -1,0 +1,333 @@
+// Multi-GPU Jacobi-PCG iteration with its exchange steps fused into the three kernels (one process per GPU, strip
+// partition).  The reference has no distributed code; this is the solve of its Newton loop
+// (Plasticity2D_DP/pythonFEM.py:1062-1066) sharded over GPUs.
+//
+// Every rank owns a small "communication block" in symmetric memory (CUDA IPC mappings, reachable by every peer through
+// NVLink/NVSwitch).  A PCG iteration needs three exchanges, and each one leaves from the kernel that produces the data
+// and is awaited by the kernel that consumes it - no collective library call, no host round trip, so the whole
+// iteration is three plain kernel launches and can be replayed from a CUDA graph:
+//
+//   A  q = K p, p'q      waits: neighbours' ghost rows of p (halo flags)      publishes: partial p'q  -> every rank
+//   B  x, r update       waits: p'q partials of all ranks                     publishes: partial {r'z, r'r} -> every rank
+//   C  p = z + beta p    waits: {r'z, r'r} partials of all ranks              publishes: interface rows of p -> neighbours
+//
+// A publication is: plain peer stores of the data, then a release store (system scope) of a sequence number to the
+// receiver's flag word; the receiver polls its own (local) flag with acquire loads.  Partials are summed by every rank
+// in rank order, so all ranks compute bit-identical alpha and beta.  The sequence number is a device-resident iteration
+// counter that only ever grows, so a graph replay needs no changing arguments.  Waits are bounded (2 s): on a time-out
+// the kernel sets an error word and carries on, so a dead peer cannot hang the GPU.
+//
+// Why overwriting is safe: rank X publishes p'q(it) at the end of A(it), i.e. after it passed the wait of C(it-1), which
+// needs every rank's B(it-1) to have ended - and B(it-1) was the last reader of the p'q(it-1) slots.  The same argument
+// covers the {r'z, r'r} slots (double-buffered by iteration parity because C(it) still needs r'z(it-1)) and the ghost rows
+// of p (written in C(it), last read by the neighbours' A(it), which ended before their B(it) published).
+#include "common.cuh"
+#include "spmv.cuh"
+
+#define FEM_PEER_MAX 16
+// layout of a communication block, in 8-byte words
+enum {
+  PW_FLAG_PQ = 0,     // [16] sequence number of rank r's latest p'q partial
+  PW_FLAG_RZ = 16,    // [16] ... of its latest {r'z, r'r} partial
+  PW_HFLAG = 32,      // [2]  ghost rows of p current: [0] written by the lower neighbour, [1] by the upper one
+  PW_SLOT_PQ = 36,    // [16] doubles
+  PW_SLOT_RZRR = 52,  // [2][16] double2 {r'z, r'r}, indexed by iteration parity
+  // words below are only touched by the owning rank
+  PW_IT = 116,        // iteration counter (monotone over the life of the block)
+  PW_TICKET = 117,    // last-block detection
+  PW_ERR = 118,       // sticky: a wait timed out
+  PW_ACC = 120,       // [3] doubles: local p'q, r'z, r'r accumulators
+  PW_OUT = 124,       // [2] doubles: global r'z and r'r of the last finished iteration (for the host's convergence check)
+  PW_WORDS = 128
+};
+
+struct PeerView {
+  uint64_t* local;
+  uint64_t* peer[FEM_PEER_MAX];  // peer[r] = rank r's block (peer[rank] == local)
+  int rank, world;
+};
+
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+#define FEM_PEER_TIMEOUT_NS 2000000000ull
+
+// Poll a flag in this rank's own block until a peer has stored a sequence number >= want.
+__device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want, uint64_t* err) {
+  if (ld_acquire_sys(flag) >= want) return;
+  if (*reinterpret_cast<volatile uint64_t*>(err)) return;  // an earlier wait already failed: do not stall again
+  const uint64_t t0 = global_timer_ns();
+  while (ld_acquire_sys(flag) < want) {
+    if (global_timer_ns() - t0 > FEM_PEER_TIMEOUT_NS) {
+      atomicExch(reinterpret_cast<unsigned long long*>(err), 1ull);
+      return;
+    }
+  }
+}
+
+// True in exactly one block of the grid: the one that arrives last.  All global writes (and atomics) a block issued
+// before the call are visible to that block afterwards.
+__device__ __forceinline__ bool arrive_last(uint64_t* ticket_word, int* sh) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ticket_word), 1u);
+    *sh = (t == gridDim.x - 1) ? 1 : 0;
+    __threadfence();
+  }
+  __syncthreads();
+  return *sh != 0;
+}
+
+// ---- A: q = K p and the partial p'q ---------------------------------------------------------------------------------
+template <int GROUP, int U>
+__global__ void __launch_bounds__(256) ppcg_spmv_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
+                                                        const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
+                                                        const double* __restrict__ p, double* __restrict__ q,
+                                                        const uint8_t* __restrict__ mask, const PeerView pv) {
+  __shared__ double red[32];
+  __shared__ int sh_last;
+  uint64_t* L = pv.local;
+  const uint64_t it = L[PW_IT];
+  // ghost rows of p: stored by the neighbours' C(it-1); nothing of p is loaded before the flags are seen
+  if (threadIdx.x == 0 && pv.rank > 0) wait_flag(L + PW_HFLAG + 0, it, L + PW_ERR);
+  if (threadIdx.x == 1 && pv.rank < pv.world - 1) wait_flag(L + PW_HFLAG + 1, it, L + PW_ERR);
+  __syncthreads();
+  double dot = spmv_rows<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, p, q, mask, true);
+  dot = block_sum(dot, red);
+  if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 0, dot);
+  if (arrive_last(L + PW_TICKET, &sh_last)) {
+    if (threadIdx.x < pv.world) {
+      const double tot = __ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 0);
+      uint64_t* dst = pv.peer[threadIdx.x];
+      reinterpret_cast<double*>(dst + PW_SLOT_PQ)[pv.rank] = tot;
+      st_release_sys(dst + PW_FLAG_PQ + pv.rank, it + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      reinterpret_cast<double*>(L + PW_ACC)[0] = 0.0;
+      *reinterpret_cast<unsigned*>(L + PW_TICKET) = 0u;
+    }
+  }
+}
+
+// ---- B: x += alpha p, r -= alpha q and the partials {r'z, r'r} -------------------------------------------------------
+__global__ void __launch_bounds__(256) ppcg_update_xr_kernel(int64_t n2, const double2* __restrict__ p, const double2* __restrict__ q,
+                                                             const double2* __restrict__ minv, double2* __restrict__ x,
+                                                             double2* __restrict__ r, const PeerView pv) {
+  __shared__ double red[32];
+  __shared__ double sh_pq[FEM_PEER_MAX], sh_rz[FEM_PEER_MAX];
+  __shared__ int sh_last;
+  uint64_t* L = pv.local;
+  const uint64_t it = L[PW_IT];
+  if (threadIdx.x < pv.world) {
+    wait_flag(L + PW_FLAG_PQ + threadIdx.x, it + 1, L + PW_ERR);
+    sh_pq[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(L + PW_SLOT_PQ) + threadIdx.x);
+    sh_rz[threadIdx.x] = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX + threadIdx.x).x;
+  }
+  __syncthreads();
+  double pq = 0.0, rz_old = 0.0;
+  for (int k = 0; k < pv.world; ++k) {  // rank order: the same sum on every rank
+    pq += sh_pq[k];
+    rz_old += sh_rz[k];
+  }
+  const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
+  double rz = 0.0, rr = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pi = p[i], qi = __ldcs(q + i), mi = minv[i];
+    double2 xi = x[i], ri = r[i];
+    xi.x = fma(alpha, pi.x, xi.x);
+    xi.y = fma(alpha, pi.y, xi.y);
+    ri.x = fma(-alpha, qi.x, ri.x);
+    ri.y = fma(-alpha, qi.y, ri.y);
+    x[i] = xi;
+    r[i] = ri;
+    rz = fma(ri.x * mi.x, ri.x, rz);
+    rz = fma(ri.y * mi.y, ri.y, rz);
+    rr = fma(ri.x, ri.x, rr);
+    rr = fma(ri.y, ri.y, rr);
+  }
+  rz = block_sum(rz, red);
+  rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 1, rz);
+    atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 2, rr);
+  }
+  if (arrive_last(L + PW_TICKET, &sh_last)) {
+    if (threadIdx.x < pv.world) {
+      const double2 tot = make_double2(__ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 1),
+                                       __ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 2));
+      uint64_t* dst = pv.peer[threadIdx.x];
+      (reinterpret_cast<double2*>(dst + PW_SLOT_RZRR) + (it & 1) * FEM_PEER_MAX)[pv.rank] = tot;
+      st_release_sys(dst + PW_FLAG_RZ + pv.rank, it + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      reinterpret_cast<double*>(L + PW_ACC)[1] = 0.0;
+      reinterpret_cast<double*>(L + PW_ACC)[2] = 0.0;
+      *reinterpret_cast<unsigned*>(L + PW_TICKET) = 0u;
+    }
+  }
+}
+
+// ---- C: p = z + beta p on the owned rows, interface rows stored straight into the neighbours' ghost rows -------------
+__global__ void __launch_bounds__(256) ppcg_update_p_kernel(int64_t own_lo, int64_t own_hi, const double2* __restrict__ r,
+                                                            const double2* __restrict__ minv, double2* __restrict__ p,
+                                                            int64_t s_up, int64_t c_up, double2* dst_up, int64_t s_lo, int64_t c_lo,
+                                                            double2* dst_lo, const PeerView pv) {
+  __shared__ double sh_new[FEM_PEER_MAX], sh_rr[FEM_PEER_MAX], sh_old[FEM_PEER_MAX];
+  __shared__ int sh_last;
+  uint64_t* L = pv.local;
+  const uint64_t it = L[PW_IT];
+  if (threadIdx.x < pv.world) {
+    wait_flag(L + PW_FLAG_RZ + threadIdx.x, it + 1, L + PW_ERR);
+    const double2 nw = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + (it & 1) * FEM_PEER_MAX + threadIdx.x);
+    sh_new[threadIdx.x] = nw.x;
+    sh_rr[threadIdx.x] = nw.y;
+    sh_old[threadIdx.x] = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX + threadIdx.x).x;
+  }
+  __syncthreads();
+  double rz_new = 0.0, rz_old = 0.0, rr = 0.0;
+  for (int k = 0; k < pv.world; ++k) {
+    rz_new += sh_new[k];
+    rz_old += sh_old[k];
+    rr += sh_rr[k];
+  }
+  const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+  bool pushed = false;
+  // ghost rows of p are never written locally: their owners store them
+  for (int64_t i = own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < own_hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 ri = r[i], mi = minv[i];
+    double2 pi = p[i];
+    pi.x = fma(beta, pi.x, mi.x * ri.x);
+    pi.y = fma(beta, pi.y, mi.y * ri.y);
+    p[i] = pi;
+    if (dst_up && i >= s_up && i < s_up + c_up) { dst_up[i - s_up] = pi; pushed = true; }
+    if (dst_lo && i >= s_lo && i < s_lo + c_lo) { dst_lo[i - s_lo] = pi; pushed = true; }
+  }
+  if (pushed) __threadfence_system();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    reinterpret_cast<double*>(L + PW_OUT)[0] = rz_new;
+    reinterpret_cast<double*>(L + PW_OUT)[1] = rr;
+  }
+  if (arrive_last(L + PW_TICKET, &sh_last)) {
+    if (threadIdx.x == 0 && pv.rank < pv.world - 1) st_release_sys(pv.peer[pv.rank + 1] + PW_HFLAG + 0, it + 1);
+    if (threadIdx.x == 1 && pv.rank > 0) st_release_sys(pv.peer[pv.rank - 1] + PW_HFLAG + 1, it + 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      L[PW_IT] = it + 1;
+      *reinterpret_cast<unsigned*>(L + PW_TICKET) = 0u;
+    }
+  }
+}
+
+// Start of a solve: the all-reduced {r'z, r'r} of the initial residual (scal[0], scal[1] of fem_pcg_init) become the
+// "previous iteration" slots; accumulators, ticket and error word are cleared.  Local stores only.
+__global__ void ppcg_begin_kernel(uint64_t* L, const double* __restrict__ scal, int world) {
+  if (threadIdx.x == 0) {
+    const uint64_t it = L[PW_IT];
+    double2* slot = reinterpret_cast<double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX;
+    for (int k = 0; k < FEM_PEER_MAX; ++k) slot[k] = make_double2(0.0, 0.0);
+    slot[0] = make_double2(scal[0], scal[1]);
+    for (int k = 0; k < 3; ++k) reinterpret_cast<double*>(L + PW_ACC)[k] = 0.0;
+    reinterpret_cast<double*>(L + PW_OUT)[0] = scal[0];
+    reinterpret_cast<double*>(L + PW_OUT)[1] = scal[1];
+    L[PW_TICKET] = 0;
+    L[PW_ERR] = 0;
+    // the halo flags already hold `it` (stored by the neighbours' last C kernel; 0 in a fresh block): the first A kernel
+    // passes at once, so the ghost rows of the initial p come from fem_halo_push followed by a host-level barrier
+  }
+}
+
+static int make_view(PeerView* pv, void* comm, const void* const* peers, int rank, int world) {
+  FEM_REQUIRE(comm && peers && world >= 1 && world <= FEM_PEER_MAX && rank >= 0 && rank < world, "peer view");
+  memset(pv, 0, sizeof(*pv));
+  pv->local = reinterpret_cast<uint64_t*>(comm);
+  for (int r = 0; r < world; ++r) {
+    FEM_REQUIRE(peers[r] != nullptr, "null peer block");
+    pv->peer[r] = reinterpret_cast<uint64_t*>(const_cast<void*>(peers[r]));
+  }
+  pv->peer[rank] = pv->local;
+  pv->rank = rank;
+  pv->world = world;
+  return FEM_OK;
+}
+
+static unsigned vec_grid(const int64_t n_items, const int sm_count) {
+  int64_t b = (n_items + 255) / 256;
+  const int64_t cap = (int64_t)(sm_count > 0 ? sm_count : 148) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+extern "C" int fem_ppcg_words(void) { return PW_WORDS; }
+
+extern "C" int fem_ppcg_begin(void* comm, const double* scal, int world, fem_stream stream) {
+  FEM_REQUIRE(comm && scal && world >= 1 && world <= FEM_PEER_MAX, "null pointer or world size");
+  ppcg_begin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint64_t*>(comm), scal, world);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_ppcg_spmv_dot(const fem_plan* P, const double* K_vals, const double* p, double* q, const uint8_t* free_mask,
+                                 void* comm, const void* const* peers, int rank, int world, fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && p && q, "null pointer");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(q) & 15u) == 0, "K_vals, p, q must be 16-byte aligned");
+  PeerView pv;
+  int rc = make_view(&pv, comm, peers, rank, world);
+  if (rc != FEM_OK) return rc;
+  const SpmvShape sh = spmv_shape(P);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PSPMV(G, UU) ppcg_spmv_kernel<G, UU><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, p, q, free_mask, pv)
+#define PSPMV_U(G) do { if (sh.unroll == 1) PSPMV(G, 1); else if (sh.unroll == 2) PSPMV(G, 2); else PSPMV(G, 4); } while (0)
+  if (sh.group == 4) PSPMV_U(4);
+  else if (sh.group == 8) PSPMV_U(8);
+  else PSPMV_U(16);
+#undef PSPMV_U
+#undef PSPMV
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_ppcg_update_xr(const fem_plan* P, const double* p, const double* q, const double* minv, double* x, double* r,
+                                  void* comm, const void* const* peers, int rank, int world, fem_stream stream) {
+  FEM_REQUIRE(P && p && q && minv && x && r, "null pointer");
+  PeerView pv;
+  int rc = make_view(&pv, comm, peers, rank, world);
+  if (rc != FEM_OK) return rc;
+  const int64_t n2 = P->n_dof / 2;
+  ppcg_update_xr_kernel<<<vec_grid(n2, P->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      n2, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q), reinterpret_cast<const double2*>(minv),
+      reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), pv);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+extern "C" int fem_ppcg_update_p(const fem_plan* P, int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p,
+                                 int64_t src_up, int64_t n_up, double* dst_up, int64_t src_lo, int64_t n_lo, double* dst_lo,
+                                 void* comm, const void* const* peers, int rank, int world, fem_stream stream) {
+  FEM_REQUIRE(P && r && minv && p && own_lo >= 0 && own_hi > own_lo && own_hi <= P->n_dof && own_lo % 2 == 0 && own_hi % 2 == 0,
+              "null pointer or bad owned range");
+  FEM_REQUIRE(src_up % 2 == 0 && src_lo % 2 == 0 && n_up % 2 == 0 && n_lo % 2 == 0, "halo ranges must be whole nodes");
+  PeerView pv;
+  int rc = make_view(&pv, comm, peers, rank, world);
+  if (rc != FEM_OK) return rc;
+  ppcg_update_p_kernel<<<vec_grid((own_hi - own_lo) / 2, P->sm_count), 256, 0, (cudaStream_t)stream>>>(
+      own_lo / 2, own_hi / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p),
+      src_up / 2, n_up / 2, reinterpret_cast<double2*>(dst_up), src_lo / 2, n_lo / 2, reinterpret_cast<double2*>(dst_lo), pv);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}

@@ -8,6 +8,7 @@
 // 1 B/nnz of indices instead of CSR's 12 B/nnz.  Row values are read as coalesced double2, x is
 // gathered as one double2 per block through L1/L2.
 #include "common.cuh"
+#include "spmv.cuh"
 
 template <int GROUP, int U>
 __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
@@ -20,77 +21,7 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
     if (zero_a) *zero_a = 0.0;
     if (zero_b) *zero_b = 0.0;
   }
-  constexpr int GPW = 32 / GROUP;  // lane groups per warp
-  const int lane = threadIdx.x & 31, sub = lane % GROUP, gi = lane / GROUP;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  constexpr int NPW = GPW * U;  // nodes per warp per sweep: U independent row pairs in flight per lane group
-  double dot = 0.0;
-  for (int64_t nb = warp_global * NPW; nb < n_n; nb += n_warps * NPW) {
-    int p0[U], deg[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t a = nb + u * GPW + gi;
-      p0[u] = 0;
-      deg[u] = 0;
-      if (a < n_n) {
-        p0[u] = __ldg(nbr_ptr + a);
-        deg[u] = __ldg(nbr_ptr + a + 1) - p0[u];
-      }
-    }
-    int m[U];
-    double2 v0[U], v1[U], xv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      m[u] = 0;
-      v0[u] = v1[u] = make_double2(0.0, 0.0);
-      if (sub < deg[u]) {
-        const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
-        m[u] = __ldg(nbr_idx + p0[u] + sub);
-        v0[u] = __ldcs(row0 + sub);
-        v1[u] = __ldcs(row0 + deg[u] + sub);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      xv[u] = make_double2(0.0, 0.0);
-      if (sub < deg[u]) xv[u] = __ldg(reinterpret_cast<const double2*>(x) + m[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      double acc0 = fma(v0[u].y, xv[u].y, v0[u].x * xv[u].x);
-      double acc1 = fma(v1[u].y, xv[u].y, v1[u].x * xv[u].x);
-      for (int j = sub + GROUP; j < deg[u]; j += GROUP) {  // rows longer than GROUP blocks
-        const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
-        const int mm = __ldg(nbr_idx + p0[u] + j);
-        const double2 w0 = __ldcs(row0 + j), w1 = __ldcs(row0 + deg[u] + j);
-        const double2 xx = __ldg(reinterpret_cast<const double2*>(x) + mm);
-        acc0 = fma(w0.x, xx.x, acc0);
-        acc0 = fma(w0.y, xx.y, acc0);
-        acc1 = fma(w1.x, xx.x, acc1);
-        acc1 = fma(w1.y, xx.y, acc1);
-      }
-#pragma unroll
-      for (int o = GROUP / 2; o > 0; o >>= 1) {
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-      }
-      const int64_t a = nb + u * GPW + gi;
-      if (sub == 0 && a < n_n) {
-        if (mask) {
-          const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
-          if (!mk.x) acc0 = 0.0;
-          if (!mk.y) acc1 = 0.0;
-        }
-        reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
-        if (dot_out) {
-          const double2 xa = __ldg(reinterpret_cast<const double2*>(x) + a);
-          dot = fma(xa.x, acc0, dot);
-          dot = fma(xa.y, acc1, dot);
-        }
-      }
-    }
-  }
+  double dot = spmv_rows<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, x, y, mask, dot_out != nullptr);
   if (dot_out) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) atomicAdd(dot_out, dot);
@@ -101,16 +32,10 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
                        double* dot, double* zero_a, double* zero_b, cudaStream_t st) {
   FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
-  const int threads = 256;
-  int group = P->max_degree <= 8 ? 4 : (P->max_degree <= 16 ? 8 : 16);  // P1: 7 blocks per row pair -> 2 per lane
-  if (g_fem_tuning.spmv_group == 4 || g_fem_tuning.spmv_group == 8 || g_fem_tuning.spmv_group == 16) group = g_fem_tuning.spmv_group;
-  int unroll = g_fem_tuning.spmv_unroll;
-  if (unroll != 1 && unroll != 2 && unroll != 4) unroll = 2;
-  int64_t blocks = (P->n_n * group / unroll + threads - 1) / threads;
-  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 8);  // persistent grid (measured best), few dot-product atomics
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-#define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<(unsigned)blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b)
+  const SpmvShape sh = spmv_shape(P);
+  const int threads = 256, group = sh.group, unroll = sh.unroll;
+  const unsigned blocks = sh.blocks;
+#define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b)
 #define SPMV_U(G) do { if (unroll == 1) SPMV(G, 1); else if (unroll == 2) SPMV(G, 2); else SPMV(G, 4); } while (0)
   if (group == 4) SPMV_U(4);
   else if (group == 8) SPMV_U(8);

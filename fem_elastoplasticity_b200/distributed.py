@@ -58,17 +58,19 @@ class StripPartition:
     def row_slice(self, v, row):
         return v[row * self.row_dofs:(row + 1) * self.row_dofs]
 
-    def halo_exchange(self, v):
-        """Fill the ghost node rows of the DOF vector ``v`` from the neighbouring strips (no-op on one rank)."""
+    def halo_exchange(self, *vs):
+        """Fill the ghost node rows of the DOF vectors ``vs`` from the neighbouring strips (no-op on one rank); all
+        vectors travel in one batched send/recv group."""
         if self.world == 1:
             return
         ops = []
-        if self.has_upper:   # my top owned row -> upper rank's bottom ghost row; its first owned row -> my top ghost row
-            ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.last_owned_row), self.rank + 1))
-            ops.append(dist.P2POp(dist.irecv, self.row_slice(v, self.last_owned_row + 1), self.rank + 1))
-        if self.has_lower:
-            ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.first_owned_row), self.rank - 1))
-            ops.append(dist.P2POp(dist.irecv, self.row_slice(v, 0), self.rank - 1))
+        for v in vs:
+            if self.has_upper:   # my top owned row -> upper rank's bottom ghost row; its first owned row -> my top ghost row
+                ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.last_owned_row), self.rank + 1))
+                ops.append(dist.P2POp(dist.irecv, self.row_slice(v, self.last_owned_row + 1), self.rank + 1))
+            if self.has_lower:
+                ops.append(dist.P2POp(dist.isend, self.row_slice(v, self.first_owned_row), self.rank - 1))
+                ops.append(dist.P2POp(dist.irecv, self.row_slice(v, 0), self.rank - 1))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
@@ -82,8 +84,9 @@ class PeerHalo:
 
     ``p`` lives in a symmetric allocation; ``fem_pcg_update_p_push`` stores this rank's interface rows into the neighbours'
     ghost rows from the kernel that computes them, and stream-ordered signals (put_signal / wait_signal) tell the neighbour
-    that its ghosts are current.  No spin-wait lives in our kernels.  Overwriting a neighbour's ghost rows is safe because the
-    all-reduce of {r'z, r'r} sits between every SpMV (the reader) and the next p update (the writer)."""
+    that its ghosts are current.  Overwriting a neighbour's ghost rows is safe because the all-reduce of {r'z, r'r} sits
+    between every SpMV (the reader) and the next p update (the writer).  With ``make_comm`` the same object also carries
+    the communication block of the fused iteration, where flags polled inside the kernels replace signals and all-reduces."""
     CHANNEL = 0
 
     def __init__(self, part, n_dof_local, device):
@@ -103,6 +106,24 @@ class PeerHalo:
         self.up = (part.last_owned_row * rd, rd, self.peers[part.rank + 1].data_ptr()) if part.has_upper else (0, 0, 0)
         self.lo = ((part.first_owned_row * rd, rd, self.peers[part.rank - 1].data_ptr() + (part.ny_loc + 1) * rd * 8)
                    if part.has_lower else (0, 0, 0))
+        self.hdl.barrier(channel=1)
+        self.comm = None
+
+    def make_comm(self, n_words):
+        """Communication block of the fused iteration (csrc/peer_pcg.cu): ``n_words`` zeroed 8-byte words in symmetric
+        memory on every rank + the table of all ranks' blocks as mapped into this process."""
+        import torch.distributed._symmetric_memory as symm
+        part = self.part
+        self.comm = symm.empty(n_words, dtype=torch.int64, device=self.buf.device)
+        self.comm.zero_()
+        self.comm_hdl = symm.rendezvous(self.comm, dist.group.WORLD)
+        self._comm_views = [self.comm if r == part.rank else self.comm_hdl.get_buffer(r, (n_words,), torch.int64) for r in range(part.world)]
+        self.comm_table = (C.c_void_p * part.world)(*[v.data_ptr() for v in self._comm_views])
+        torch.cuda.synchronize()
+        self.comm_hdl.barrier(channel=0)                 # every block is zeroed before any peer may store into it
+        torch.cuda.synchronize()
+
+    def barrier(self):
         self.hdl.barrier(channel=1)
 
     def push_args(self):
@@ -161,6 +182,22 @@ class CudaOps:
     def spmv(self, k, x, y, mask, dot):
         self.plan.spmv(k, x, mask=mask, out=y, dot=dot)
 
+    # fused multi-GPU iteration: exchanges inside the kernels (peer stores + flags), see csrc/peer_pcg.cu
+    def ppcg_words(self):
+        from ._lib import load
+        return int(load().fem_ppcg_words())
+
+    def ppcg_begin(self, peer, scal):
+        self._call("fem_ppcg_begin", self._ptr(peer.comm), self._ptr(scal), peer.part.world, self._stream())
+
+    def ppcg_iteration(self, peer, k, p, q, mask, minv, x, r, own):
+        part = peer.part
+        tail = (self._ptr(peer.comm), peer.comm_table, part.rank, part.world, self._stream())
+        self._call("fem_ppcg_spmv_dot", self.plan._h, self._ptr(k), self._ptr(p), self._ptr(q), self._ptr(mask), *tail)
+        self._call("fem_ppcg_update_xr", self.plan._h, self._ptr(p), self._ptr(q), self._ptr(minv), self._ptr(x), self._ptr(r), *tail)
+        self._call("fem_ppcg_update_p", self.plan._h, int(own[0]), int(own[1]), self._ptr(r), self._ptr(minv), self._ptr(p),
+                   *peer.push_args(), *tail)
+
 
 class DistributedPCG:
     """Jacobi-PCG over a strip partition.  ``ops`` defaults to the CUDA kernels; the CPU tests inject a
@@ -175,18 +212,26 @@ class DistributedPCG:
         # send/recv + all-reduces captured inside the graph a full-size 2-GPU run hung (round-1 finding), so multi-rank
         # runs launch eagerly.
         self.use_graph = bool(use_graph) and ops is None and part.world == 1
+        self.use_graph_fused = bool(use_graph)           # the fused iteration has no library call inside: capturable on any world size
         self._graph, self._graph_key = None, None
-        # halo of p: NCCL send/recv (default; measured as fast at 8 GPUs) or NVLink peer stores fused into the p-update kernel
+        # exchanges of the iteration: peer=False NCCL send/recv + all-reduces; True: halo as NVLink peer stores fused into the
+        # p-update kernel, NCCL all-reduces; "fused": halo and both reductions inside the three kernels (csrc/peer_pcg.cu,
+        # fastest: 0.122 vs 0.212 ms/iteration at 8 GPUs x 2M DOFs); "auto": fused, NCCL if symmetric memory is unavailable
         self.peer = None
-        if ops is None and part.world > 1 and peer in ("auto", True):
+        self.fused = False
+        if ops is None and part.world > 1 and peer in ("auto", True, "fused"):
             try:
                 self.peer = PeerHalo(part, self.ops.n, self.r.device)
                 self.p = self.peer.p
+                if peer in ("fused", "auto"):
+                    self.peer.make_comm(self.ops.ppcg_words())
+                    self.fused = True
             except Exception as e:                       # symmetric memory unavailable: keep the NCCL path
-                if peer is True:
+                if peer in (True, "fused"):
                     raise
                 self.peer_error = repr(e)
-                self.peer = None
+                self.peer, self.fused = None, False
+                self.p = o.new_vec()
         self.scal = o.new_vec(8)
         self.en = o.new_vec(3)
         self.owned = part.owned_mask(self.r.device)
@@ -200,6 +245,8 @@ class DistributedPCG:
         o.pcg_init(rhs, None, self.mask, self.minv, self.r, self.p, scal)
         part.all_reduce(scal[0:5])
         n_it = iters if iters is not None else maxit
+        if self.fused:
+            return self._solve_fused(k_vals, n_it, iters is None, rtol, check_every)
         it = 0
         self.launches_last = 3
         peer = self.peer
@@ -240,6 +287,60 @@ class DistributedPCG:
         part.halo_exchange(self.x)
         return self.x, it
 
+    GRAPH_CHUNK = 10
+
+    def _solve_fused(self, k_vals, n_it, check, rtol, check_every):
+        """Iterations with the exchanges inside the kernels (csrc/peer_pcg.cu): no collective call per iteration.  After
+        one eagerly launched chunk the same launches are captured (capturing does not execute) and replayed from a CUDA
+        graph; the iteration index lives on the device, so one graph serves every iteration."""
+        o, part, peer = self.ops, self.part, self.peer
+        own = part.owned_dof_range()
+        o.ppcg_begin(peer, self.scal)
+        o.halo_push(self.p, peer.push_args())            # ghosts of the initial search direction
+        peer.barrier()
+        self.launches_last = 5
+        out = peer.comm.view(torch.float64)[124:126]     # global r'z, r'r of the last finished iteration
+        bb = None
+
+        def chunk(n):
+            for _ in range(n):
+                o.ppcg_iteration(peer, k_vals, self.p, self.q, self.mask, self.minv, self.x, self.r, own)
+
+        g, it, c = None, 0, self.GRAPH_CHUNK
+        key = (k_vals.data_ptr(), self.p.data_ptr())
+        if self._graph is not None and self._graph_key == key:
+            g = self._graph
+        while it < n_it:
+            n = min(c, n_it - it)
+            if check:
+                n = min(n, check_every - it % check_every)
+            if g is not None and n == c:
+                g.replay()
+            else:
+                chunk(n)
+                if self.use_graph_fused and g is None and n == c and it + 2 * c <= n_it:
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            chunk(c)
+                        self._graph, self._graph_key = g, key
+                    except Exception as e:               # capture unsupported: eager launches
+                        self.graph_error, self.use_graph_fused, g = repr(e), False, None
+            it += n
+            self.launches_last += 3 * n
+            if check and it % check_every == 0:
+                if bb is None:
+                    bb = float(self.scal[4].item())
+                rr = float(out[1].item())
+                if rr != rr or rr == float("inf"):
+                    raise ArithmeticError("PCG breakdown: residual is not finite")
+                if rr <= rtol * rtol * bb:
+                    break
+        if int(peer.comm[118].item()) != 0:
+            raise RuntimeError("fused PCG: a peer did not publish within 2 s (rank %d)" % part.rank)
+        part.halo_exchange(self.x)
+        return self.x, it
+
     def _pair_graph(self, k_vals, iteration):
         """CUDA graph of iterations (0, 1) - the kernels only depend on the parity of the iteration index.  Captured after
         one eager pair (NCCL communicators / lazy initialisation must not happen under capture); cached per matrix buffer."""
@@ -268,8 +369,8 @@ class DistributedPCG:
     def energy_norms(self, k_vals, v0, v1, v2):
         """v_i' K v_i over the whole (distributed) DOF set; returns a device tensor of 3 doubles."""
         self.en.zero_()
+        self.part.halo_exchange(v0, v1, v2)
         for i, v in enumerate((v0, v1, v2)):
-            self.part.halo_exchange(v)
             self.ops.spmv(k_vals, v, self.q, self.owned, self.en[i:i + 1])
         self.part.all_reduce(self.en)
         return self.en

@@ -144,6 +144,27 @@ int fem_halo_push(const double* v, int64_t src0, int64_t n0, double* dst0, int64
                   fem_stream stream);
 int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p, double* scal, int iter,
                           int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1, fem_stream stream);
+/* Fused multi-GPU PCG iteration (csrc/peer_pcg.cu): the three exchanges of an iteration (ghost rows of p, p'q, {r'z, r'r})
+ * leave from the kernel that produces them as NVLink peer stores + release flags and are awaited (bounded spin on a local
+ * flag) by the kernel that consumes them.  No collective call and no host round trip inside an iteration, so the three
+ * launches are CUDA-graph capturable; all ranks sum the partials in rank order and get bit-identical alpha and beta.
+ * comm: this rank's communication block, fem_ppcg_words() 8-byte words of symmetric (peer-mapped) memory, zero-filled once
+ *   at allocation; peers[r] = rank r's block as mapped into this process (host array of `world` device pointers, <= 16).
+ * fem_ppcg_begin: call after fem_pcg_init and the all-reduce of scal[0:5]; loads {r'z, r'r} = scal[0:2] (local stores).
+ *   The ghost rows of the initial p must be in place (fem_halo_push + a barrier across ranks) before the first iteration.
+ * One iteration = fem_ppcg_spmv_dot, fem_ppcg_update_xr, fem_ppcg_update_p, the same number on every rank.
+ * fem_ppcg_update_p: [own_lo, own_hi) = owned DOF range; p[src_up : src_up+n_up] is also stored to dst_up (the upper
+ *   neighbour's ghost row, NULL if none), likewise *_lo.  Words 124/125 of comm then hold the global r'z and r'r (doubles)
+ *   and word 118 is non-zero if a wait timed out (2 s; the results are then invalid).                         */
+int fem_ppcg_words(void);
+int fem_ppcg_begin(void* comm, const double* scal, int world, fem_stream stream);
+int fem_ppcg_spmv_dot(const fem_plan* plan, const double* K_vals, const double* p, double* q, const uint8_t* free_mask,
+                      void* comm, const void* const* peers, int rank, int world, fem_stream stream);
+int fem_ppcg_update_xr(const fem_plan* plan, const double* p, const double* q, const double* minv, double* x, double* r,
+                       void* comm, const void* const* peers, int rank, int world, fem_stream stream);
+int fem_ppcg_update_p(const fem_plan* plan, int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p,
+                      int64_t src_up, int64_t n_up, double* dst_up, int64_t src_lo, int64_t n_lo, double* dst_lo,
+                      void* comm, const void* const* peers, int rank, int world, fem_stream stream);
 /* Single-GPU Jacobi-PCG on K[Q,Q] x[Q] = rhs[Q], x[~Q] left untouched at 0.  work: 4*n_dof doubles.
  * Stops when |r| <= rtol*|rhs| (checked every check_every iterations).  Synchronises.            */
 int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const uint8_t* free_mask, double rtol,

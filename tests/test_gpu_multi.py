@@ -1,5 +1,5 @@
-"""Two-GPU test of the distributed PCG (NCCL halo and NVLink peer-memory halo): both must reproduce the single-GPU
-solve.  Skipped when fewer than two CUDA devices are visible (the driver's `pytest -m gpu` box has one)."""
+"""Two-GPU test of the distributed PCG (NCCL halo, NVLink peer-memory halo, and the fused iteration whose three exchanges
+live inside the kernels): all must reproduce the single-GPU solve.  Skipped when fewer than two CUDA devices are visible (the driver's `pytest -m gpu` box has one)."""
 import os
 import socket
 
@@ -41,12 +41,18 @@ def _worker(rank, world, port, nx, ny, out_dir):
     lo = part.iy0 * part.row_dofs
     rhs = torch.as_tensor(b_global[lo:lo + P.n_dof].copy()).to(dev)
     res = {}
-    for name, peer, graph in (("nccl", False, False), ("peer", True, False)):
+    for name, peer, graph in (("nccl", False, False), ("peer", True, False), ("fused", "fused", True)):
         pcg = DistributedPCG(P, part, mask, peer=peer, use_graph=graph)
         x, its = pcg.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=25)
         res[name] = x.cpu().numpy().copy()
         res[name + "_its"] = its
         res[name + "_is_peer"] = pcg.peer is not None
+        if name in ("nccl", "fused"):                     # a second solve on the same object, fixed iteration count
+            x, n2 = pcg.solve(k, 2.0 * rhs, iters=70)
+            res[name + "_second"] = x.cpu().numpy().copy()
+            assert n2 == 70
+        if name == "fused":
+            assert pcg.fused and pcg._graph is not None, getattr(pcg, "graph_error", "fused iteration was not captured")
     from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
     tl = TwoLevelPCG(P, mask, nc=8, part=part)
     x, its, rel = tl.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=5)
@@ -75,15 +81,19 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
     b = np.random.default_rng(9).standard_normal(P.n_dof)
     ref, its, rel = P.pcg(k, b, P.mask_u8(m["Q"]), rtol=1e-12, maxit=20000, check_every=25)
     ref = ref.cpu().numpy()
-    for name in ("nccl", "peer", "twolevel"):
+    for name in ("nccl", "peer", "fused", "twolevel"):
         got = np.full_like(ref, np.nan)
         for r in range(world):
             d = np.load(tmp_path / f"r{r}.npz")
             lo, (a, e) = int(d["lo"]), d["own"]
             got[lo + a:lo + e] = d[name][a:e]
             assert d[name + "_its"] > 0
-            if name == "peer":
-                assert bool(d["peer_is_peer"]), "symmetric-memory halo was not active"
+            if name in ("peer", "fused"):
+                assert bool(d[name + "_is_peer"]), "symmetric-memory halo was not active"
+            if name == "fused":                           # same iteration, exchanges inside the kernels: same iterates
+                assert int(d["fused_its"]) == int(d["nccl_its"])
+                sa, sb = d["fused_second"][a:e], d["nccl_second"][a:e]
+                np.testing.assert_allclose(sa, sb, rtol=1e-8, atol=1e-10 * np.abs(sb).max())
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
     assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 2   # H/h = 24 here
