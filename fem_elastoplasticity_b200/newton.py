@@ -7,7 +7,12 @@
 Reference: Plasticity2D_DP/pythonFEM.py:1040-1087 (Newton), :986-1131 (footing load stepping);
 tsx-tunnel/pythonFEM.py:1763-1830.  The dense LAPACK solve (:1066) is replaced by PCG driven to
 ``pcg_rtol``; everything else follows the reference statement by statement.  Host Python only sequences
-kernel launches and reads back one scalar (the criterion) per iteration."""
+kernel launches and reads back one scalar (the criterion) per iteration.
+
+With a ``distributed.StripPartition`` the same loop runs one process per GPU: every rank keeps its strip of
+the mesh plus one ghost cell row, so strain, return map, assembly and internal force need no communication and its owned
+rows are complete; the linear solve is ``DistributedPCG`` (exchanges inside its kernels over NVLink peer memory) and the
+criterion, plastic-point count and footing pressure are all-reduced, so every rank takes the same branches."""
 import numpy as np
 import torch
 
@@ -16,13 +21,20 @@ from .plan import FemPlan, axpby, dp_return_map
 
 class NewtonSolver:
     def __init__(self, plan: FemPlan, shear, bulk, eta, c, q_mask, pcg_rtol=1e-13, pcg_maxit=200000, check_every=50,
-                 tangent_mode="direct", precond="jacobi", coarse_cells=64):
+                 tangent_mode="direct", precond="jacobi", coarse_cells=64, part=None, halo="auto"):
         self.plan = plan
         dev = plan.device
         f = plan._f64
         self.shear, self.bulk = f(shear, (plan.n_int,)), f(bulk, (plan.n_int,))
         self.eta, self.c = f(eta, (plan.n_int,)), f(c, (plan.n_int,))
-        self.mask = plan.mask_u8(q_mask)
+        self.free = plan.mask_u8(q_mask)                   # free (non-Dirichlet) DOFs of the local vectors, ghosts included
+        self.mask = self.free
+        self.part = part if (part is not None and part.world > 1) else None
+        self._dpcg = None
+        if self.part is not None:                          # unknowns of this rank: free AND owned
+            from .distributed import DistributedPCG
+            self.mask = self.free & part.owned_mask(dev)
+            self._dpcg = DistributedPCG(plan, part, self.mask, peer=halo)
         self.pcg_rtol, self.pcg_maxit, self.check_every = pcg_rtol, pcg_maxit, check_every
         self.tangent_mode = tangent_mode
         self.precond, self.coarse_cells, self._tl = precond, coarse_cells, None   # "jacobi" | "twolevel" (see twolevel.py)
@@ -47,16 +59,32 @@ class NewtonSolver:
         if self.precond == "twolevel":
             if self._tl is None:                          # coarse operator of K_elast, kept for every tangent solve
                 from .twolevel import TwoLevelPCG
-                self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells).setup(self.k_elast)
+                self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells, part=self.part).setup(self.k_elast)
             x, its, rel = self._tl.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=min(self.check_every, 10))
             return x.clone(), its, rel
+        if self._dpcg is not None:                        # ghost rows of the returned vector are current
+            x, its = self._dpcg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every)
+            return x.clone(), its, None
         return self.plan.pcg(k_vals, rhs, self.mask, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every,
                              x0=x0, work=self.work)
 
     def criterion(self, du, u_it, u_new):
         """q1/(q2+q3) with q = sqrt(v' K_elast v)   (Plasticity2D_DP/pythonFEM.py:1072-1075)"""
-        q = np.sqrt(self.plan.energy_norms(self.k_elast, du, u_it, u_new, work=self.tmp).cpu().numpy())
+        if self._dpcg is not None:
+            q = np.sqrt(self._dpcg.energy_norms(self.k_elast, du, u_it, u_new).cpu().numpy())
+        else:
+            q = np.sqrt(self.plan.energy_norms(self.k_elast, du, u_it, u_new, work=self.tmp).cpu().numpy())
         return float(q[0] / (q[1] + q[2]))
+
+    def plastic_points(self, r):
+        """Number of yielding integration points (the reference prints it per return-map call); owned elements only,
+        summed over the ranks, when distributed."""
+        if self.part is None:
+            return int(r["counts"].sum().item())
+        n_own = self.part.n_e_owned * self.plan.n_q
+        n = (r["ind_p"][:n_own] != 0).sum().to(torch.int64).reshape(1)
+        self.part.all_reduce(n)
+        return int(n.item())
 
     def iteration(self, u_it, ep_old, e0=None):
         """One semismooth Newton iteration (:1043-1075). Returns (u_new, criterion, n_plastic, pcg_iterations)."""
@@ -71,15 +99,17 @@ class NewtonSolver:
         du, its, rel = self.solve(self.k_tan, self.rhs)
         u_new = axpby(1.0, u_it, 1.0, du)
         crit = self.criterion(du, u_it, u_new)
-        n_plast = int(r["counts"].sum().item())
+        n_plast = self.plastic_points(r)
         self.last = {"pcg_iters": its, "pcg_relres": rel, "n_plast": n_plast, "criterion": crit}
         return u_new, crit, n_plast, its
 
 
 def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi",
-                   coarse_cells=64):
+                   coarse_cells=64, part=None, halo="auto"):
     """Strip-footing load stepping of Plasticity2D_DP.elasticity_fem (:986-1131) on the device.
-    ``mesh``: dict with coordinates (2,n_n), elements (3,n_e), Q, dirichlet_nodes (NumPy or CUDA tensors)."""
+    ``mesh``: dict with coordinates (2,n_n), elements (3,n_e), Q, dirichlet_nodes (NumPy or CUDA tensors).
+    ``part``: a distributed.StripPartition when run one process per GPU; ``mesh`` is then this rank's ``part.local_mesh``
+    and the returned U / Ep are the local arrays (owned rows + ghosts)."""
     from . import pythonFEM as api
     from .meshgen import footing_materials
     et = api.LagrangeElementType.P1
@@ -89,10 +119,13 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
     dev = P.device
     G, Kb, eta, c = footing_materials(P.n_int, dev)
     c0 = 450
-    ns = NewtonSolver(P, G, Kb, eta, c, mesh["Q"], pcg_rtol=pcg_rtol, tangent_mode=tangent_mode, precond=precond, coarse_cells=coarse_cells)
+    ns = NewtonSolver(P, G, Kb, eta, c, mesh["Q"], pcg_rtol=pcg_rtol, tangent_mode=tangent_mode, precond=precond, coarse_cells=coarse_cells,
+                      part=part, halo=halo)
     dn = torch.as_tensor(np.asarray(mesh["dirichlet_nodes"].cpu() if isinstance(mesh["dirichlet_nodes"], torch.Tensor)
                                     else mesh["dirichlet_nodes"], dtype=np.float64)).to(dev)
     q_nd = dn[1] > 0
+    if ns.part is not None:                                          # footing nodes this rank owns
+        q_nd = q_nd & part.owned_mask(dev)[0::2].bool()
     dn_flat = dn.t().reshape(-1).contiguous()
     d_zeta = 1 / 1000
     d_zeta_min, d_zeta_old = d_zeta / 1300, d_zeta
@@ -101,7 +134,7 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
     f = P.spmv(ns.k_elast, ud)                                       # f = -K_elast Ud   (:998)
     axpby(-1.0, f, 0.0, f, out=f)
     sol, _, _ = ns.solve(ns.k_elast, f)
-    mk = ns.mask.bool()
+    mk = ns.free.bool()
     u_it = torch.where(mk, sol, ud)                                  # :1004 (free DOFs overwritten)
     U = torch.zeros_like(u_it)
     u_old = axpby(-1.0, u_it, 0.0, u_it)                             # :1009
@@ -127,7 +160,12 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
             zeta_old, d_zeta_old = zeta, d_zeta
             step += 1
             pa = P.transform(r["s"][1])
-            pressure = float((-pa[q_nd].mean() / c0).item())
+            if ns.part is None:
+                pressure = float((-pa[q_nd].mean() / c0).item())
+            else:                                                     # mean over the footing nodes of all ranks
+                acc = torch.stack([pa[q_nd].sum(), q_nd.sum().to(torch.float64)])
+                part.all_reduce(acc)
+                pressure = float((-(acc[0] / acc[1]) / c0).item())
             hist.append((zeta, pressure))
             if pressure - pressure_old < 0.1 and criterion < 1e-12:
                 d_zeta *= 2

@@ -99,6 +99,55 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
     assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 2   # H/h = 24 here
 
 
+def _newton_worker(rank, world, port, nx, ny, steps, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fem_elastoplasticity_b200 import newton
+    from fem_elastoplasticity_b200.distributed import StripPartition
+    part = StripPartition(nx, ny, rank, world, size_x=10.0, size_y=10.0)
+    out = newton.footing_driver(part.local_mesh(dev), max_steps=steps, pcg_rtol=1e-12, part=part)
+    a, e = part.first_owned_row * (nx + 1), (part.last_owned_row + 1) * (nx + 1)        # owned local nodes
+    np.savez(os.path.join(out_dir, f"n{rank}.npz"), U=out["U"][:, a:e], node0=part.iy0 * (nx + 1) + a, steps=out["steps"],
+             trace=np.array(out["trace"], dtype=float), hist=np.array(out["hist"], dtype=float),
+             ep=out["Ep"][:, :part.n_e_owned], elem0=2 * nx * part.iy0)
+    dist.destroy_process_group()
+
+
+def test_two_gpu_footing_newton_matches_single_gpu(tmp_path):
+    """The whole load-stepping Newton loop sharded over two GPUs (strip partition, fused PCG exchanges, all-reduced
+    criterion / plastic count / footing pressure) follows the single-GPU run: same branches, same displacements."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    from fem_elastoplasticity_b200 import meshgen, newton
+    nx, ny, world, steps = 40, 48, 2, 6
+    mp.spawn(_newton_worker, args=(world, _free_port(), nx, ny, steps, str(tmp_path)), nprocs=world, join=True)
+    ref = newton.footing_driver(meshgen.square_mesh_p1(nx, ny, 10.0, 10.0), max_steps=steps, pcg_rtol=1e-12)
+    rt = np.array(ref["trace"], dtype=float)
+    U = np.full_like(ref["U"], np.nan)
+    ep = np.full_like(ref["Ep"], np.nan)
+    for r in range(world):
+        d = np.load(tmp_path / f"n{r}.npz")
+        assert int(d["steps"]) == ref["steps"]
+        t = d["trace"]
+        assert t.shape == rt.shape, "same number of Newton iterations on every rank as on one GPU"
+        assert np.array_equal(t[:, :3], rt[:, :3])                     # load factor, iteration index, plastic points
+        np.testing.assert_allclose(t[:, 3], rt[:, 3], rtol=1e-4, atol=1e-11)
+        np.testing.assert_allclose(d["hist"], np.array(ref["hist"], dtype=float), rtol=1e-8)
+        n0, e0 = int(d["node0"]), int(d["elem0"])
+        U[:, n0:n0 + d["U"].shape[1]] = d["U"]
+        ep[:, e0:e0 + d["ep"].shape[1]] = d["ep"]
+    assert not np.isnan(U).any() and not np.isnan(ep).any()
+    print("plastic points per Newton iteration:", rt[:, 2].astype(int).tolist())
+    np.testing.assert_allclose(U, ref["U"], rtol=1e-7, atol=1e-9 * np.abs(ref["U"]).max())
+    np.testing.assert_allclose(ep, ref["Ep"], rtol=1e-6, atol=1e-9 * max(np.abs(ref["Ep"]).max(), 1e-30))
+
+
 def test_single_rank_graph_pcg_matches_c_loop():
     """World size 1: the Python-sequenced PCG (CUDA-graph replay of iteration pairs, and eager) equals fem_pcg."""
     import torch
