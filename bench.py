@@ -263,12 +263,15 @@ def run_gpu(args):
         return b0.elapsed_time(b1) / reps
     t_tan_only = iso(lambda: P.assemble_tangent(rm["ds"], out=k_tan))
     t_el_only = iso(lambda: P.assemble_elastic(G, Kb, out=k_el))
-    # ---- one CONVERGED inner solve (rtol 1e-10) of the step's system with the two-level preconditioner (single rank)
+    # ---- one CONVERGED inner solve (rtol 1e-10) of the step's system with the two-level preconditioner (on N > 1 ranks:
+    # coarse operator all-reduced and replicated, halo + reductions through NCCL)
     conv = None
-    if world == 1 and not args.no_converged_solve:
+    if not args.no_converged_solve:
         from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
-        tl = TwoLevelPCG(P, mask, nc=args.coarse_cells).setup(k_el)
+        tl = TwoLevelPCG(P, mask, nc=args.coarse_cells, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"])).setup(k_el)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         c0 = time.perf_counter()
         _, c_its, c_rel = tl.solve(k_tan, rhs, rtol=1e-10, maxit=50000, check_every=50)
         torch.cuda.synchronize()
@@ -276,7 +279,7 @@ def run_gpu(args):
         conv = {"preconditioner": f"two-level: Jacobi + {tl.grid[4]}x{tl.grid[5]} bilinear coarse grid ({tl.ncd} coarse DOFs, dense inverse)",
                 "rtol": 1e-10, "iterations": c_its, "relres": c_rel, "seconds": c_s, "ms_per_iteration": 1e3 * c_s / max(c_its, 1),
                 "coarse_setup_seconds": tl.setup_seconds,
-                "jacobi_reference": "57 500 iterations / 41.7 s for the footing's elastic solve on this mesh (tools/full_solve.py)"}
+                "jacobi_reference": "57 500 iterations / 41.7 s for the footing's elastic solve on the 16M-element mesh, one GPU (tools/full_solve.py)"}
         del tl
     # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned); every step uploads its DS
     # (H2D) and downloads its K values (D2H) inside the timed region.  Two steps are in flight on two streams with

@@ -58,7 +58,7 @@ SIGNATURES = {
     "fem_ppcg_update_xr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
     "fem_ppcg_update_p": [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.POINTER(_vp), _i32, _i32, _vp],
     "fem_pcg": [_vp, _vp, _vp, _vp, _dbl, _i32, _i32, _vp, _vp, C.POINTER(_i32), C.POINTER(_dbl), _vp],
-    "fem_coarse_galerkin": [_vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp],
+    "fem_coarse_galerkin": [_vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp],
     "fem_dense_gemv": [_i32, _vp, _vp, _vp, _vp, _vp],
     "fem_tl_init": [_i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp],
     "fem_tl_update_xr": [_i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
@@ -87,6 +87,10 @@ def load():
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, C.c_int)
     _lib = lib
+    for kv in filter(None, os.environ.get("FEM_B200_TUNING", "").split(",")):      # launch-shape / diagnostic knobs: "key=value,..."
+        k, v = kv.split("=")
+        if lib.fem_set_tuning(k.strip().encode(), int(v)) != 0:
+            raise ValueError(f"FEM_B200_TUNING: unknown key {k!r}")
     return lib
 
 

@@ -27,6 +27,7 @@ struct FemTuning {
   int spmv_blocks_per_sm;  // 0 = 32
   int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D)
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
+  int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
 };
 extern FemTuning g_fem_tuning;
 

@@ -11,40 +11,44 @@
 //   B  x, r update       waits: p'q partials of all ranks                     publishes: partial {r'z, r'r} -> every rank
 //   C  p = z + beta p    waits: {r'z, r'r} partials of all ranks              publishes: interface rows of p -> neighbours
 //
-// A publication is: plain peer stores of the data, then a release store (system scope) of a sequence number to the
-// receiver's flag word; the receiver polls its own (local) flag with acquire loads.  Partials are summed by every rank
-// in rank order, so all ranks compute bit-identical alpha and beta.  The sequence number is a device-resident iteration
-// counter that only ever grows, so a graph replay needs no changing arguments.  Waits are bounded (2 s): on a time-out
-// the kernel sets an error word and carries on, so a dead peer cannot hang the GPU.
+// The scalar partials travel as self-validating 16-byte lines {value.lo, seq, value.hi, seq} (one vector store; the
+// receiver polls its own copy until both sequence words match), so neither side needs a system-scope fence.  The
+// interface rows of p are bulk data: plain peer stores, fence, then a release store of the sequence number to the
+// neighbour's flag word - issued by the few blocks that own those rows, which run FIRST in kernel C, so the flag is
+// long there when the neighbour's next SpMV starts.  Partials are summed by every rank in rank order, so all ranks
+// compute bit-identical alpha and beta.  The sequence number is a device-resident iteration counter that only ever
+// grows, so a graph replay needs no changing arguments.  Waits are bounded (2 s): on a time-out the kernel sets an
+// error word and carries on, so a dead peer cannot hang the GPU.
 //
 // Why overwriting is safe: rank X publishes p'q(it) at the end of A(it), i.e. after it passed the wait of C(it-1), which
-// needs every rank's B(it-1) to have ended - and B(it-1) was the last reader of the p'q(it-1) slots.  The same argument
-// covers the {r'z, r'r} slots (double-buffered by iteration parity because C(it) still needs r'z(it-1)) and the ghost rows
+// needs every rank's B(it-1) to have ended - and B(it-1) was the last reader of the p'q(it-1) lines.  The same argument
+// covers the {r'z, r'r} lines (double-buffered by iteration parity because C(it) still needs r'z(it-1)) and the ghost rows
 // of p (written in C(it), last read by the neighbours' A(it), which ended before their B(it) published).
 #include "common.cuh"
 #include "spmv.cuh"
 
 #define FEM_PEER_MAX 16
-// layout of a communication block, in 8-byte words
+// layout of a communication block, in 8-byte words (FEM_PPCG_WORD_* in the header mirror ERR and OUT)
 enum {
-  PW_FLAG_PQ = 0,     // [16] sequence number of rank r's latest p'q partial
-  PW_FLAG_RZ = 16,    // [16] ... of its latest {r'z, r'r} partial
-  PW_HFLAG = 32,      // [2]  ghost rows of p current: [0] written by the lower neighbour, [1] by the upper one
-  PW_SLOT_PQ = 36,    // [16] doubles
-  PW_SLOT_RZRR = 52,  // [2][16] double2 {r'z, r'r}, indexed by iteration parity
+  PW_LL_PQ = 0,       // [16][2]    line of rank r's p'q partial
+  PW_LL_RZ = 32,      // [2][16][4] lines of rank r's {r'z, r'r} partials, indexed by iteration parity
+  PW_HFLAG = 160,     // [2]  ghost rows of p current: [0] written by the lower neighbour, [1] by the upper one
   // words below are only touched by the owning rank
-  PW_IT = 116,        // iteration counter (monotone over the life of the block)
-  PW_TICKET = 117,    // last-block detection
-  PW_ERR = 118,       // sticky: a wait timed out
-  PW_ACC = 120,       // [3] doubles: local p'q, r'z, r'r accumulators
-  PW_OUT = 124,       // [2] doubles: global r'z and r'r of the last finished iteration (for the host's convergence check)
-  PW_WORDS = 128
+  PW_IT = 164,        // iteration counter (monotone over the life of the block)
+  PW_TICKET = 165,    // last-block detection
+  PW_TICKET_HALO = 166,  // ... among the blocks that push the interface rows
+  PW_ERR = FEM_PPCG_WORD_ERR,  // sticky: a wait timed out
+  PW_ACC = 168,       // [3] doubles: local p'q, r'z, r'r accumulators
+  PW_OUT = FEM_PPCG_WORD_OUT,  // [2] doubles: global r'z and r'r of the last finished iteration (for the host's convergence check)
+  PW_WORDS = FEM_PPCG_WORDS
 };
+static_assert(PW_ERR == 167 && PW_OUT == 172 && PW_WORDS >= 174, "communication block layout");
 
 struct PeerView {
   uint64_t* local;
   uint64_t* peer[FEM_PEER_MAX];  // peer[r] = rank r's block (peer[rank] == local)
   int rank, world;
+  int nowait;  // diagnostic: never spin (see FemTuning::peer_nowait)
 };
 
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
@@ -64,8 +68,8 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 #define FEM_PEER_TIMEOUT_NS 2000000000ull
 
 // Poll a flag in this rank's own block until a peer has stored a sequence number >= want.
-__device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want, uint64_t* err) {
-  if (ld_acquire_sys(flag) >= want) return;
+__device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want, uint64_t* err, const int nowait) {
+  if (ld_acquire_sys(flag) >= want || nowait) return;
   if (*reinterpret_cast<volatile uint64_t*>(err)) return;  // an earlier wait already failed: do not stall again
   const uint64_t t0 = global_timer_ns();
   while (ld_acquire_sys(flag) < want) {
@@ -76,14 +80,42 @@ __device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want
   }
 }
 
-// True in exactly one block of the grid: the one that arrives last.  All global writes (and atomics) a block issued
-// before the call are visible to that block afterwards.
-__device__ __forceinline__ bool arrive_last(uint64_t* ticket_word, int* sh) {
-  __threadfence();
+// 16-byte line {lo, seq, hi, seq}: whichever way the fabric splits the store into 8-byte pieces, a reader that sees
+// both sequence words equal to the one it expects has both halves of the value.
+__device__ __forceinline__ void line_store(uint64_t* line, const double v, const uint32_t seq) {
+  const uint64_t b = (uint64_t)__double_as_longlong(v);
+  const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool line_try(const uint64_t* line, const uint32_t seq, double* v) {
+  uint32_t lo, f0, hi, f1;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(line) : "memory");
+  *v = __longlong_as_double((long long)(((uint64_t)hi << 32) | lo));
+  return f0 == seq && f1 == seq;
+}
+__device__ __noinline__ double line_wait(const uint64_t* line, const uint32_t seq, uint64_t* err, const int nowait) {
+  double v;
+  if (line_try(line, seq, &v) || nowait) return v;
+  if (*reinterpret_cast<volatile uint64_t*>(err)) return 0.0;
+  const uint64_t t0 = global_timer_ns();
+  while (!line_try(line, seq, &v)) {
+    if (global_timer_ns() - t0 > FEM_PEER_TIMEOUT_NS) {
+      atomicExch(reinterpret_cast<unsigned long long*>(err), 1ull);
+      return 0.0;
+    }
+  }
+  return v;
+}
+
+// True in exactly one block among the `n_blocks` that call it: the one that arrives last.  What thread 0 of a block
+// wrote or accumulated (atomics) before the call is visible to that block afterwards; other threads' plain stores are
+// only ordered by the kernel boundary (or by their own system fence, for the interface rows).
+__device__ __forceinline__ bool arrive_last(uint64_t* ticket_word, const unsigned n_blocks, int* sh) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ticket_word), 1u);
-    *sh = (t == gridDim.x - 1) ? 1 : 0;
+    *sh = (t == n_blocks - 1) ? 1 : 0;
     __threadfence();
   }
   __syncthreads();
@@ -101,18 +133,16 @@ __global__ void __launch_bounds__(256) ppcg_spmv_kernel(int64_t n_n, const int32
   uint64_t* L = pv.local;
   const uint64_t it = L[PW_IT];
   // ghost rows of p: stored by the neighbours' C(it-1); nothing of p is loaded before the flags are seen
-  if (threadIdx.x == 0 && pv.rank > 0) wait_flag(L + PW_HFLAG + 0, it, L + PW_ERR);
-  if (threadIdx.x == 1 && pv.rank < pv.world - 1) wait_flag(L + PW_HFLAG + 1, it, L + PW_ERR);
+  if (threadIdx.x == 0 && pv.rank > 0) wait_flag(L + PW_HFLAG + 0, it, L + PW_ERR, pv.nowait);
+  if (threadIdx.x == 32 && pv.rank < pv.world - 1) wait_flag(L + PW_HFLAG + 1, it, L + PW_ERR, pv.nowait);  // another warp: both polls in flight
   __syncthreads();
   double dot = spmv_rows<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, p, q, mask, true);
   dot = block_sum(dot, red);
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 0, dot);
-  if (arrive_last(L + PW_TICKET, &sh_last)) {
+  if (arrive_last(L + PW_TICKET, gridDim.x, &sh_last)) {
     if (threadIdx.x < pv.world) {
       const double tot = __ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 0);
-      uint64_t* dst = pv.peer[threadIdx.x];
-      reinterpret_cast<double*>(dst + PW_SLOT_PQ)[pv.rank] = tot;
-      st_release_sys(dst + PW_FLAG_PQ + pv.rank, it + 1);
+      line_store(pv.peer[threadIdx.x] + PW_LL_PQ + 2 * pv.rank, tot, (uint32_t)(it + 1));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -131,10 +161,10 @@ __global__ void __launch_bounds__(256) ppcg_update_xr_kernel(int64_t n2, const d
   __shared__ int sh_last;
   uint64_t* L = pv.local;
   const uint64_t it = L[PW_IT];
-  if (threadIdx.x < pv.world) {
-    wait_flag(L + PW_FLAG_PQ + threadIdx.x, it + 1, L + PW_ERR);
-    sh_pq[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(L + PW_SLOT_PQ) + threadIdx.x);
-    sh_rz[threadIdx.x] = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX + threadIdx.x).x;
+  {  // one warp per quantity, one lane per rank: all lines are polled concurrently
+    const int w = threadIdx.x >> 5, k = threadIdx.x & 31;
+    if (w == 0 && k < pv.world) sh_pq[k] = line_wait(L + PW_LL_PQ + 2 * k, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
+    if (w == 1 && k < pv.world) sh_rz[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait);
   }
   __syncthreads();
   double pq = 0.0, rz_old = 0.0;
@@ -164,13 +194,11 @@ __global__ void __launch_bounds__(256) ppcg_update_xr_kernel(int64_t n2, const d
     atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 1, rz);
     atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 2, rr);
   }
-  if (arrive_last(L + PW_TICKET, &sh_last)) {
-    if (threadIdx.x < pv.world) {
-      const double2 tot = make_double2(__ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 1),
-                                       __ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 2));
-      uint64_t* dst = pv.peer[threadIdx.x];
-      (reinterpret_cast<double2*>(dst + PW_SLOT_RZRR) + (it & 1) * FEM_PEER_MAX)[pv.rank] = tot;
-      st_release_sys(dst + PW_FLAG_RZ + pv.rank, it + 1);
+  if (arrive_last(L + PW_TICKET, gridDim.x, &sh_last)) {
+    if (threadIdx.x < 2 * pv.world) {  // thread 2r: r'z to rank r, thread 2r+1: r'r to rank r
+      const int dst_rank = threadIdx.x >> 1, which = threadIdx.x & 1;
+      const double tot = __ldcg(reinterpret_cast<const double*>(L + PW_ACC) + 1 + which);
+      line_store(pv.peer[dst_rank] + PW_LL_RZ + (it & 1) * 4 * FEM_PEER_MAX + 4 * pv.rank + 2 * which, tot, (uint32_t)(it + 1));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -182,20 +210,22 @@ __global__ void __launch_bounds__(256) ppcg_update_xr_kernel(int64_t n2, const d
 }
 
 // ---- C: p = z + beta p on the owned rows, interface rows stored straight into the neighbours' ghost rows -------------
+// The first n_halo_blocks blocks do the interface rows only (one item per thread): their flag leaves early and their
+// system fence overlaps with the other blocks' work.
 __global__ void __launch_bounds__(256) ppcg_update_p_kernel(int64_t own_lo, int64_t own_hi, const double2* __restrict__ r,
                                                             const double2* __restrict__ minv, double2* __restrict__ p,
                                                             int64_t s_up, int64_t c_up, double2* dst_up, int64_t s_lo, int64_t c_lo,
-                                                            double2* dst_lo, const PeerView pv) {
+                                                            double2* dst_lo, unsigned n_halo_blocks, const PeerView pv) {
   __shared__ double sh_new[FEM_PEER_MAX], sh_rr[FEM_PEER_MAX], sh_old[FEM_PEER_MAX];
   __shared__ int sh_last;
   uint64_t* L = pv.local;
   const uint64_t it = L[PW_IT];
-  if (threadIdx.x < pv.world) {
-    wait_flag(L + PW_FLAG_RZ + threadIdx.x, it + 1, L + PW_ERR);
-    const double2 nw = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + (it & 1) * FEM_PEER_MAX + threadIdx.x);
-    sh_new[threadIdx.x] = nw.x;
-    sh_rr[threadIdx.x] = nw.y;
-    sh_old[threadIdx.x] = __ldcg(reinterpret_cast<const double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX + threadIdx.x).x;
+  {
+    const int w = threadIdx.x >> 5, k = threadIdx.x & 31;
+    const uint64_t* nw = L + PW_LL_RZ + (it & 1) * 4 * FEM_PEER_MAX + 4 * k;
+    if (w == 0 && k < pv.world) sh_new[k] = line_wait(nw, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
+    if (w == 1 && k < pv.world) sh_rr[k] = line_wait(nw + 2, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
+    if (w == 2 && k < pv.world) sh_old[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait);
   }
   __syncthreads();
   double rz_new = 0.0, rz_old = 0.0, rr = 0.0;
@@ -205,26 +235,43 @@ __global__ void __launch_bounds__(256) ppcg_update_p_kernel(int64_t own_lo, int6
     rr += sh_rr[k];
   }
   const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
-  bool pushed = false;
-  // ghost rows of p are never written locally: their owners store them
-  for (int64_t i = own_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < own_hi; i += (int64_t)gridDim.x * blockDim.x) {
-    const double2 ri = r[i], mi = minv[i];
-    double2 pi = p[i];
-    pi.x = fma(beta, pi.x, mi.x * ri.x);
-    pi.y = fma(beta, pi.y, mi.y * ri.y);
-    p[i] = pi;
-    if (dst_up && i >= s_up && i < s_up + c_up) { dst_up[i - s_up] = pi; pushed = true; }
-    if (dst_lo && i >= s_lo && i < s_lo + c_lo) { dst_lo[i - s_lo] = pi; pushed = true; }
+  if (blockIdx.x < n_halo_blocks) {  // interface rows: item j < c_up goes up, the rest goes down
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < c_up + c_lo) {
+      const bool up = j < c_up;
+      const int64_t i = up ? s_up + j : s_lo + (j - c_up);
+      const double2 ri = r[i], mi = minv[i];
+      double2 pi = p[i];
+      pi.x = fma(beta, pi.x, mi.x * ri.x);
+      pi.y = fma(beta, pi.y, mi.y * ri.y);
+      p[i] = pi;
+      if (up) dst_up[j] = pi;
+      else dst_lo[j - c_up] = pi;
+      __threadfence_system();
+    }
+    if (arrive_last(L + PW_TICKET_HALO, n_halo_blocks, &sh_last)) {
+      if (threadIdx.x == 0 && c_up > 0) st_release_sys(pv.peer[pv.rank + 1] + PW_HFLAG + 0, it + 1);
+      if (threadIdx.x == 1 && c_lo > 0) st_release_sys(pv.peer[pv.rank - 1] + PW_HFLAG + 1, it + 1);
+      if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(L + PW_TICKET_HALO) = 0u;
+    }
   }
-  if (pushed) __threadfence_system();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  // the rest of the owned range, on the other blocks (the interface blocks are left to their fence and flag); ghost
+  // rows of p are never written locally (their owners store them)
+  const int64_t n_rest = (int64_t)gridDim.x - n_halo_blocks;
+  if (blockIdx.x >= n_halo_blocks)
+    for (int64_t i = own_lo + ((int64_t)blockIdx.x - n_halo_blocks) * blockDim.x + threadIdx.x; i < own_hi; i += n_rest * blockDim.x) {
+      if ((i >= s_up && i < s_up + c_up) || (i >= s_lo && i < s_lo + c_lo)) continue;
+      const double2 ri = r[i], mi = minv[i];
+      double2 pi = p[i];
+      pi.x = fma(beta, pi.x, mi.x * ri.x);
+      pi.y = fma(beta, pi.y, mi.y * ri.y);
+      p[i] = pi;
+    }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
     reinterpret_cast<double*>(L + PW_OUT)[0] = rz_new;
     reinterpret_cast<double*>(L + PW_OUT)[1] = rr;
   }
-  if (arrive_last(L + PW_TICKET, &sh_last)) {
-    if (threadIdx.x == 0 && pv.rank < pv.world - 1) st_release_sys(pv.peer[pv.rank + 1] + PW_HFLAG + 0, it + 1);
-    if (threadIdx.x == 1 && pv.rank > 0) st_release_sys(pv.peer[pv.rank - 1] + PW_HFLAG + 1, it + 1);
-    __syncthreads();
+  if (arrive_last(L + PW_TICKET, gridDim.x, &sh_last)) {  // every block has read the iteration counter: advance it
     if (threadIdx.x == 0) {
       L[PW_IT] = it + 1;
       *reinterpret_cast<unsigned*>(L + PW_TICKET) = 0u;
@@ -237,13 +284,16 @@ __global__ void __launch_bounds__(256) ppcg_update_p_kernel(int64_t own_lo, int6
 __global__ void ppcg_begin_kernel(uint64_t* L, const double* __restrict__ scal, int world) {
   if (threadIdx.x == 0) {
     const uint64_t it = L[PW_IT];
-    double2* slot = reinterpret_cast<double2*>(L + PW_SLOT_RZRR) + ((it + 1) & 1) * FEM_PEER_MAX;
-    for (int k = 0; k < FEM_PEER_MAX; ++k) slot[k] = make_double2(0.0, 0.0);
-    slot[0] = make_double2(scal[0], scal[1]);
+    uint64_t* lines = L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX;
+    for (int k = 0; k < FEM_PEER_MAX; ++k) {
+      line_store(lines + 4 * k, k == 0 ? scal[0] : 0.0, (uint32_t)it);
+      line_store(lines + 4 * k + 2, k == 0 ? scal[1] : 0.0, (uint32_t)it);
+    }
     for (int k = 0; k < 3; ++k) reinterpret_cast<double*>(L + PW_ACC)[k] = 0.0;
     reinterpret_cast<double*>(L + PW_OUT)[0] = scal[0];
     reinterpret_cast<double*>(L + PW_OUT)[1] = scal[1];
     L[PW_TICKET] = 0;
+    L[PW_TICKET_HALO] = 0;
     L[PW_ERR] = 0;
     // the halo flags already hold `it` (stored by the neighbours' last C kernel; 0 in a fresh block): the first A kernel
     // passes at once, so the ghost rows of the initial p come from fem_halo_push followed by a host-level barrier
@@ -261,6 +311,7 @@ static int make_view(PeerView* pv, void* comm, const void* const* peers, int ran
   pv->peer[rank] = pv->local;
   pv->rank = rank;
   pv->world = world;
+  pv->nowait = g_fem_tuning.peer_nowait;
   return FEM_OK;
 }
 
@@ -325,9 +376,14 @@ extern "C" int fem_ppcg_update_p(const fem_plan* P, int64_t own_lo, int64_t own_
   PeerView pv;
   int rc = make_view(&pv, comm, peers, rank, world);
   if (rc != FEM_OK) return rc;
-  ppcg_update_p_kernel<<<vec_grid((own_hi - own_lo) / 2, P->sm_count), 256, 0, (cudaStream_t)stream>>>(
+  if (!dst_up) n_up = 0;
+  if (!dst_lo) n_lo = 0;
+  FEM_REQUIRE((n_up == 0 || rank < world - 1) && (n_lo == 0 || rank > 0), "halo destination without a neighbour on that side");
+  const unsigned n_halo_blocks = (unsigned)((n_up / 2 + n_lo / 2 + 255) / 256);
+  const unsigned grid = n_halo_blocks + vec_grid((own_hi - own_lo) / 2, P->sm_count);
+  ppcg_update_p_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       own_lo / 2, own_hi / 2, reinterpret_cast<const double2*>(r), reinterpret_cast<const double2*>(minv), reinterpret_cast<double2*>(p),
-      src_up / 2, n_up / 2, reinterpret_cast<double2*>(dst_up), src_lo / 2, n_lo / 2, reinterpret_cast<double2*>(dst_lo), pv);
+      src_up / 2, n_up / 2, reinterpret_cast<double2*>(dst_up), src_lo / 2, n_lo / 2, reinterpret_cast<double2*>(dst_lo), n_halo_blocks, pv);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

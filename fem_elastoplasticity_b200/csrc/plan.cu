@@ -19,7 +19,7 @@ void fem_set_error(const char* fmt, ...) {
 extern "C" const char* fem_last_error_string(void) { return g_err; }
 extern "C" int fem_version(void) { return 100; }
 
-FemTuning g_fem_tuning = {0, 0, 0, 0, 0, 0};
+FemTuning g_fem_tuning = {};
 extern "C" int fem_set_tuning(const char* key, int value) {
   FEM_REQUIRE(key != nullptr, "key");
   if (!strcmp(key, "return_map_variant")) g_fem_tuning.return_map_variant = value;
@@ -28,6 +28,7 @@ extern "C" int fem_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "spmv_blocks_per_sm")) g_fem_tuning.spmv_blocks_per_sm = value;
   else if (!strcmp(key, "assemble_variant")) g_fem_tuning.assemble_variant = value;
   else if (!strcmp(key, "spmv_unroll")) g_fem_tuning.spmv_unroll = value;
+  else if (!strcmp(key, "peer_nowait")) g_fem_tuning.peer_nowait = value;
   else {
     fem_set_error("unknown tuning key %s", key);
     return FEM_ERR_INVALID_ARG;

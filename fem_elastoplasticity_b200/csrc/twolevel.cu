@@ -36,7 +36,8 @@ __device__ __forceinline__ int coarse_of(const CoarseGrid& g, double x, double y
 // ---- A_c = P^T K P (once per matrix) ---------------------------------------------------------------------------
 __global__ void coarse_galerkin_kernel(int64_t n_n, CoarseGrid g, const int32_t* __restrict__ nbr_ptr,
                                        const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
-                                       const uint8_t* __restrict__ mask, const double* __restrict__ coord, double* Ac, int ncd) {
+                                       const uint8_t* __restrict__ mask, const uint8_t* __restrict__ cmask,
+                                       const double* __restrict__ coord, double* Ac, int ncd) {
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_n; a += (int64_t)gridDim.x * blockDim.x) {
     double wi[4], wj[4];
     int ii[4], ij[4];
@@ -48,7 +49,7 @@ __global__ void coarse_galerkin_kernel(int64_t n_n, CoarseGrid g, const int32_t*
     for (int j = 0; j < deg; ++j) {
       const int b = nbr_idx[p0 + j];
       coarse_of(g, coord[b], coord[n_n + b], wj, ij);
-      const double mj0 = mask ? (double)(mask[2 * b] != 0) : 1.0, mj1 = mask ? (double)(mask[2 * b + 1] != 0) : 1.0;
+      const double mj0 = cmask ? (double)(cmask[2 * b] != 0) : 1.0, mj1 = cmask ? (double)(cmask[2 * b + 1] != 0) : 1.0;
       const double a00 = row0[2 * j] * mi0 * mj0, a01 = row0[2 * j + 1] * mi0 * mj1;
       const double a10 = row1[2 * j] * mi1 * mj0, a11 = row1[2 * j + 1] * mi1 * mj1;
 #pragma unroll
@@ -280,15 +281,17 @@ static int make_grid(CoarseGrid& g, double x0, double y0, double hx, double hy, 
   return FEM_OK;
 }
 
-extern "C" int fem_coarse_galerkin(const fem_plan* P, const double* K_vals, const uint8_t* free_mask, const double* coord, double x0,
-                                   double y0, double hx, double hy, int ncx, int ncy, double* Ac, fem_stream stream) {
+extern "C" int fem_coarse_galerkin(const fem_plan* P, const double* K_vals, const uint8_t* row_mask, const uint8_t* col_mask,
+                                   const double* coord, double x0, double y0, double hx, double hy, int ncx, int ncy, double* Ac,
+                                   fem_stream stream) {
   FEM_REQUIRE(P && K_vals && coord && Ac, "null pointer");
   CoarseGrid g;
   if (int rc = make_grid(g, x0, y0, hx, hy, ncx, ncy)) return rc;
   const int ncd = 2 * (ncx + 1) * (ncy + 1);
   cudaStream_t st = (cudaStream_t)stream;
   FEM_CUDA_CHECK(cudaMemsetAsync(Ac, 0, sizeof(double) * (size_t)ncd * ncd, st));
-  coarse_galerkin_kernel<<<tl_grid(P->n_n) * 4, 256, 0, st>>>(P->n_n, g, P->nbr_ptr, P->nbr_idx, K_vals, free_mask, coord, Ac, ncd);
+  coarse_galerkin_kernel<<<tl_grid(P->n_n) * 4, 256, 0, st>>>(P->n_n, g, P->nbr_ptr, P->nbr_idx, K_vals, row_mask,
+                                                              col_mask ? col_mask : row_mask, coord, Ac, ncd);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

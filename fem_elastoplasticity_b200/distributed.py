@@ -288,6 +288,7 @@ class DistributedPCG:
         return self.x, it
 
     GRAPH_CHUNK = 10
+    WORD_ERR, WORD_OUT = 167, 172                     # FEM_PPCG_WORD_ERR / FEM_PPCG_WORD_OUT of include/fem_b200.h
 
     def _solve_fused(self, k_vals, n_it, check, rtol, check_every):
         """Iterations with the exchanges inside the kernels (csrc/peer_pcg.cu): no collective call per iteration.  After
@@ -299,7 +300,7 @@ class DistributedPCG:
         o.halo_push(self.p, peer.push_args())            # ghosts of the initial search direction
         peer.barrier()
         self.launches_last = 5
-        out = peer.comm.view(torch.float64)[124:126]     # global r'z, r'r of the last finished iteration
+        out = peer.comm.view(torch.float64)[self.WORD_OUT:self.WORD_OUT + 2]     # global r'z, r'r of the last finished iteration
         bb = None
 
         def chunk(n):
@@ -336,7 +337,7 @@ class DistributedPCG:
                     raise ArithmeticError("PCG breakdown: residual is not finite")
                 if rr <= rtol * rtol * bb:
                     break
-        if int(peer.comm[118].item()) != 0:
+        if int(peer.comm[self.WORD_ERR].item()) != 0:
             raise RuntimeError("fused PCG: a peer did not publish within 2 s (rank %d)" % part.rank)
         part.halo_exchange(self.x)
         return self.x, it

@@ -59,7 +59,7 @@ class NewtonSolver:
         if self.precond == "twolevel":
             if self._tl is None:                          # coarse operator of K_elast, kept for every tangent solve
                 from .twolevel import TwoLevelPCG
-                self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells, part=self.part).setup(self.k_elast)
+                self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells, part=self.part, free_mask=self.free).setup(self.k_elast)
             x, its, rel = self._tl.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=min(self.check_every, 10))
             return x.clone(), its, rel
         if self._dpcg is not None:                        # ghost rows of the returned vector are current

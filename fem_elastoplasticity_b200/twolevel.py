@@ -15,8 +15,14 @@ from .plan import _ptr, _stream
 
 
 class TwoLevelPCG:
-    def __init__(self, plan, mask, nc=64, part=None, max_coarse_dofs=12000):
+    def __init__(self, plan, mask, nc=64, part=None, max_coarse_dofs=12000, free_mask=None):
+        """``mask``: the unknowns of this rank (free DOFs; free AND owned on a strip partition).  ``free_mask``: all free
+        DOFs of the local vectors, ghost rows included (needed on a partition: the Galerkin product couples owned rows to
+        ghost columns); ``nc``: coarse cells along the shorter side of the bounding box."""
         self.plan, self.mask, self.part = plan, mask, part
+        self.free_mask = free_mask
+        if part is not None and part.world > 1 and free_mask is None:
+            raise ValueError("TwoLevelPCG on a partition needs free_mask (free DOFs including ghost rows)")
         dev = plan.device
         co = plan.coord
         lo = torch.stack([co[0].min(), co[1].min()])
@@ -27,7 +33,7 @@ class TwoLevelPCG:
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         (x0, y0), (x1, y1) = lo.tolist(), hi.tolist()
         lx, ly = max(x1 - x0, 1e-300), max(y1 - y0, 1e-300)
-        ncx, ncy = (nc, max(1, round(nc * ly / lx))) if lx >= ly else (max(1, round(nc * lx / ly)), nc)
+        ncx, ncy = (max(1, round(nc * lx / ly)), nc) if lx >= ly else (nc, max(1, round(nc * ly / lx)))
         while 2 * (ncx + 1) * (ncy + 1) > max_coarse_dofs:      # keep the dense inverse small (n_c^2 doubles)
             ncx, ncy = max(1, int(ncx * 0.9)), max(1, int(ncy * 0.9))
         self.grid = (float(x0), float(y0), float(lx / ncx), float(ly / ncy), int(ncx), int(ncy))
@@ -50,7 +56,7 @@ class TwoLevelPCG:
         t0 = time.perf_counter()
         P = self.plan
         Ac = torch.empty((self.ncd, self.ncd), dtype=torch.float64, device=P.device)
-        call("fem_coarse_galerkin", P._h, _ptr(k_vals), _ptr(self.mask), _ptr(P.coord), *self.grid, _ptr(Ac), _stream())
+        call("fem_coarse_galerkin", P._h, _ptr(k_vals), _ptr(self.mask), _ptr(self.free_mask), _ptr(P.coord), *self.grid, _ptr(Ac), _stream())
         self._reduce(Ac)
         Ac = 0.5 * (Ac + Ac.t())
         d = torch.diagonal(Ac)

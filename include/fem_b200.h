@@ -145,8 +145,8 @@ int fem_halo_push(const double* v, int64_t src0, int64_t n0, double* dst0, int64
 int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const double* minv, double* p, double* scal, int iter,
                           int64_t src0, int64_t n0, double* dst0, int64_t src1, int64_t n1, double* dst1, fem_stream stream);
 /* Fused multi-GPU PCG iteration (csrc/peer_pcg.cu): the three exchanges of an iteration (ghost rows of p, p'q, {r'z, r'r})
- * leave from the kernel that produces them as NVLink peer stores + release flags and are awaited (bounded spin on a local
- * flag) by the kernel that consumes them.  No collective call and no host round trip inside an iteration, so the three
+ * leave from the kernel that produces them as NVLink peer stores (scalars as self-validating 16-byte lines, interface rows
+ * followed by a release flag) and are awaited (bounded spin on local memory) by the kernel that consumes them.  No collective call and no host round trip inside an iteration, so the three
  * launches are CUDA-graph capturable; all ranks sum the partials in rank order and get bit-identical alpha and beta.
  * comm: this rank's communication block, fem_ppcg_words() 8-byte words of symmetric (peer-mapped) memory, zero-filled once
  *   at allocation; peers[r] = rank r's block as mapped into this process (host array of `world` device pointers, <= 16).
@@ -154,8 +154,11 @@ int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const
  *   The ghost rows of the initial p must be in place (fem_halo_push + a barrier across ranks) before the first iteration.
  * One iteration = fem_ppcg_spmv_dot, fem_ppcg_update_xr, fem_ppcg_update_p, the same number on every rank.
  * fem_ppcg_update_p: [own_lo, own_hi) = owned DOF range; p[src_up : src_up+n_up] is also stored to dst_up (the upper
- *   neighbour's ghost row, NULL if none), likewise *_lo.  Words 124/125 of comm then hold the global r'z and r'r (doubles)
- *   and word 118 is non-zero if a wait timed out (2 s; the results are then invalid).                         */
+ *   neighbour's ghost row, NULL if none), likewise *_lo.  Words FEM_PPCG_WORD_OUT, +1 of comm then hold the global r'z and
+ *   r'r (doubles) and word FEM_PPCG_WORD_ERR is non-zero if a wait timed out (2 s; the results are then invalid).                         */
+#define FEM_PPCG_WORDS 176     /* 8-byte words of a communication block */
+#define FEM_PPCG_WORD_ERR 167  /* non-zero: a wait timed out */
+#define FEM_PPCG_WORD_OUT 172  /* two doubles: global r'z, r'r after the last finished iteration */
 int fem_ppcg_words(void);
 int fem_ppcg_begin(void* comm, const double* scal, int world, fem_stream stream);
 int fem_ppcg_spmv_dot(const fem_plan* plan, const double* K_vals, const double* p, double* q, const uint8_t* free_mask,
@@ -173,7 +176,9 @@ int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const
 /* ---- two-level additive preconditioner M^-1 = D^-1 + P A_c^-1 P^T (csrc/twolevel.cu) ---------------------------------
  * P: bilinear interpolation from a coarse grid of ncx x ncy cells of size hx x hy with origin (x0, y0) laid over the mesh's
  * bounding box to the fine nodes (coord = the (2, n_n) coordinates), Dirichlet rows zeroed; n_c = 2 (ncx+1)(ncy+1).
- * fem_coarse_galerkin: Ac[n_c][n_c] = P^T K P (zero-filled by the call, accumulated with FP64 atomics; once per matrix).
+ * fem_coarse_galerkin: Ac[n_c][n_c] = P_row^T K P_col (zero-filled by the call, accumulated with FP64 atomics; once per matrix);
+ *   P_row keeps the DOFs of row_mask, P_col those of col_mask (NULL = row_mask).  One GPU: both the free DOFs.  Strip-partitioned:
+ *   row_mask = free AND owned, col_mask = free (ghost columns included), and the ranks' matrices are summed.
  * fem_dense_gemv: y = A x, dense row-major (applies the inverted coarse operator); if dot != NULL, *dot += x'y.
  * r'z is never formed by a pass of its own: r'z = r'D^-1 r + r'(P z_c) and r'(P z_c) = (P^T r)'z_c = rc'zc, so
  * fem_tl_init: r = mask (rhs - Kx0) (Kx0 nullable), rc = P^T r, scal[1] = r'r, scal[4] = |rhs|^2, scal[0] = r'D^-1 r
@@ -182,8 +187,9 @@ int fem_pcg(const fem_plan* plan, const double* K_vals, const double* rhs, const
  *   fem_pcg_update_xr); the coarse GEMV then adds rc'zc to the same slot through its `dot` argument;
  * fem_tl_apply: z = minv r + P zc;  mode 0: scal[slot] += r'z (checks);  mode 1: p = z;  mode 2: p = z + beta p.
  * Together with fem_pcg_spmv_dot these are the steps of the preconditioned CG; the host sequences them.                  */
-int fem_coarse_galerkin(const fem_plan* plan, const double* K_vals, const uint8_t* free_mask, const double* coord, double x0,
-                        double y0, double hx, double hy, int ncx, int ncy, double* Ac, fem_stream stream);
+int fem_coarse_galerkin(const fem_plan* plan, const double* K_vals, const uint8_t* row_mask, const uint8_t* col_mask,
+                        const double* coord, double x0, double y0, double hx, double hy, int ncx, int ncy, double* Ac,
+                        fem_stream stream);
 int fem_dense_gemv(int n, const double* A, const double* x, double* y, double* dot, fem_stream stream);
 int fem_tl_init(int64_t n_n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv, const double* coord,
                 double x0, double y0, double hx, double hy, int ncx, int ncy, double* r, double* rc, double* scal, fem_stream stream);

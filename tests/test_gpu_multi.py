@@ -54,7 +54,7 @@ def _worker(rank, world, port, nx, ny, out_dir):
         if name == "fused":
             assert pcg.fused and pcg._graph is not None, getattr(pcg, "graph_error", "fused iteration was not captured")
     from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
-    tl = TwoLevelPCG(P, mask, nc=8, part=part)
+    tl = TwoLevelPCG(P, mask, nc=8, part=part, free_mask=P.mask_u8(mesh["Q"]))
     x, its, rel = tl.solve(k, rhs.clone(), rtol=1e-12, maxit=20000, check_every=5)
     res["twolevel"], res["twolevel_its"], res["twolevel_is_peer"] = x.cpu().numpy().copy(), its, False
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, own=np.array(part.owned_dof_range()), **res)
@@ -96,7 +96,13 @@ def test_two_gpu_pcg_matches_single_gpu(tmp_path):
                 np.testing.assert_allclose(sa, sb, rtol=1e-8, atol=1e-10 * np.abs(sb).max())
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
-    assert int(np.load(tmp_path / "r0.npz")["twolevel_its"]) < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 2   # H/h = 24 here
+    tl_its = int(np.load(tmp_path / "r0.npz")["twolevel_its"])
+    assert tl_its < int(np.load(tmp_path / "r0.npz")["nccl_its"]) // 2
+    # the partitioned coarse operator (owned rows x free columns, summed over ranks) is the single-domain one: same count
+    from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+    _, one_its, _ = TwoLevelPCG(P, P.mask_u8(m["Q"]), nc=8).solve(k, torch.as_tensor(b).cuda(), rtol=1e-12, maxit=20000, check_every=5)
+    print("two-level iterations: 2 GPUs", tl_its, "1 GPU", one_its)
+    assert abs(tl_its - one_its) <= max(5, one_its // 10)
 
 
 def _newton_worker(rank, world, port, nx, ny, steps, out_dir):
