@@ -1,4 +1,4 @@
-"""Synthetic uniform P1 meshes built directly in HBM (BASELINE.json configs 4/5).
+"""Synthetic uniform P1 meshes built directly in HBM (BASELINE.json configs 4/5) and the P1 -> P2 midpoint enrichment.
 
 Numbering is the reference's get_nodes_1 (Plasticity2D_DP/pythonFEM.py:73-122): node id = ix + iy*(n_x+1),
 cell (ix, iy) -> triangles (V1,V2,V4), (V2,V3,V4), cell-major with ix fastest; footing boundary conditions
@@ -50,3 +50,47 @@ def synthetic_strain(n_int, device="cuda", seed=0, mean=(-3e-4, -3e-4, 0.0), std
     e = torch.randn((3, n_int), generator=g, dtype=torch.float64, device=device) * std
     e += torch.tensor(mean, dtype=torch.float64, device=device)[:, None]
     return e
+
+
+def create_midpoints_p2(coord, elem):
+    """P1 -> P2 enrichment with the numbering of the reference's create_midpoints_P2 (tsx-tunnel/pythonFEM.py:1508-1626),
+    without its O(n_e^2) ``np.where`` walk: every edge is keyed by its vertex pair, a midpoint is numbered by the FIRST
+    (element, edge) visit of the reference's loop (edges in the order V2-V3, V3-V1, V1-V2), i.e. by the rank of the smallest
+    occurrence index ``3*element + edge`` among the unique keys - one sort instead of a search per edge.  Runs on whatever
+    device ``coord``/``elem`` live on (torch tensors; (2, n_n) float64, (3, n_e) integer, 0-based, counter-clockwise).
+
+    Returns tensors named like the reference's dict: coord_mid (2, n_mid), surf (3, n_boundary_edges) = (second vertex,
+    first vertex, midpoint) per boundary edge, coord_ext, elem_ext (6, n_e), elem_ed (3, n_e) midpoint index per element
+    edge, edge_el (2, 2*n_e) the elements on either side of each midpoint (0 where the reference leaves its zeros).
+    The reference finds the neighbour's edge slot from the position of one shared vertex, which presumes that the two
+    triangles traverse the edge in opposite directions; a mesh where they do not is rejected here."""
+    elem = elem.to(torch.int64)
+    dev = elem.device
+    n_e, n_n = elem.shape[1], coord.shape[1]
+    a = torch.stack([elem[1], elem[2], elem[0]], dim=1).reshape(-1)      # occurrence o = 3*element + edge: from vertex
+    b = torch.stack([elem[2], elem[0], elem[1]], dim=1).reshape(-1)      # ... to vertex
+    key = torch.minimum(a, b) * n_n + torch.maximum(a, b)
+    uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+    if int(cnt.max()) > 2:
+        raise ValueError("an edge is shared by more than two triangles")
+    occ = torch.arange(3 * n_e, device=dev)
+    first = torch.full((uniq.numel(),), 3 * n_e, dtype=torch.int64, device=dev).scatter_reduce(0, inv, occ, reduce="amin")
+    last = torch.full((uniq.numel(),), -1, dtype=torch.int64, device=dev).scatter_reduce(0, inv, occ, reduce="amax")
+    shared = cnt == 2
+    if not bool(((a[first] == b[last]) & (b[first] == a[last]))[shared].all()):
+        raise ValueError("inconsistently oriented triangles: the reference's neighbour-slot rule is undefined")
+    order = torch.argsort(first)                                         # unique edges in the order the reference meets them
+    n_mid = order.numel()
+    ind_of_edge = torch.empty_like(order)
+    ind_of_edge[order] = torch.arange(n_mid, device=dev)
+    ind = ind_of_edge[inv].reshape(n_e, 3).t()                           # (3, n_e): midpoint index of every element edge
+    fa, fb = a[first[order]], b[first[order]]
+    coord_mid = (coord[:, fa] + coord[:, fb]) / 2
+    edge_el = torch.zeros((2, max(2 * n_e, n_mid)), dtype=torch.float64, device=dev)   # reference: (2, 2 n_e), enough for n_e >= boundary edges
+    edge_el[0, :n_mid] = (first[order] // 3).to(torch.float64)
+    edge_el[1, :n_mid] = torch.where(shared[order], last[order] // 3, torch.zeros_like(order)).to(torch.float64)
+    bnd = ~shared[order]
+    mids = torch.arange(n_mid, device=dev)[bnd] + n_n
+    surf = torch.stack([fb[bnd], fa[bnd], mids]).to(torch.float64)
+    return {"coord_mid": coord_mid, "surf": surf, "coord_ext": torch.cat([coord, coord_mid], dim=1),
+            "elem_ext": torch.cat([elem, ind + n_n], dim=0), "elem_ed": ind.to(torch.float64), "edge_el": edge_el}

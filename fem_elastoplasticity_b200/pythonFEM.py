@@ -223,3 +223,23 @@ def stopping_criterion(K_elast, dU, U_it, U_new):
     v = [plan._f64(np.asarray(a, dtype=np.float64).reshape(-1, order='F')) for a in (dU, U_it, U_new)]
     q = torch.sqrt(plan.energy_norms(K_elast._fem_vals, *v)).cpu().numpy()
     return q[0] / (q[1] + q[2])
+
+
+def create_midpoints_P2(coord, elem, device=None):
+    """tsx-tunnel/pythonFEM.py:1508-1626: P1 -> P2 enrichment, same dict (keys, shapes, dtypes, midpoint numbering) as the
+    reference; computed by ``meshgen.create_midpoints_p2`` (one sort over the edges instead of the reference's
+    O(n_e^2) search) on ``device`` (default: CUDA when available)."""
+    from .meshgen import create_midpoints_p2
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    d = create_midpoints_p2(torch.as_tensor(np.ascontiguousarray(coord, dtype=np.float64)).to(dev),
+                            torch.as_tensor(np.ascontiguousarray(elem).astype(np.int64)).to(dev))
+    out = {k: v.cpu().numpy() for k, v in d.items()}
+    out["elem_ext"] = out["elem_ext"].astype(int)
+    return out
+
+
+def create_midpoints(elem_type, coord, elem, device=None):
+    """tsx-tunnel/pythonFEM.py:1629-1633 (P2 only; P4 is out of scope)."""
+    if elem_type == LagrangeElementType.P2:
+        return create_midpoints_P2(coord, elem, device=device)
+    raise NotImplementedError("only the P2 enrichment is provided")
