@@ -243,3 +243,42 @@ def create_midpoints(elem_type, coord, elem, device=None):
     if elem_type == LagrangeElementType.P2:
         return create_midpoints_P2(coord, elem, device=device)
     raise NotImplementedError("only the P2 enrichment is provided")
+
+
+# ---- load vectors of the linear-elastic demo (Elasticity2D/pythonFEM.py) ------------------------------
+def get_quadrature_surface(el_type):
+    """Elasticity2D/pythonFEM.py:112-132 -> (Xi_s (n_q_s,), WF_s (n_q_s,))."""
+    pt = 1 / np.sqrt(3)
+    if el_type in (LagrangeElementType.P1, LagrangeElementType.Q1):
+        return np.array([0]), np.array([2])
+    return np.array([-pt, pt]), np.array([1, 1])
+
+
+def get_local_basis_surface(el_type, xi_s):
+    """Elasticity2D/pythonFEM.py:212-243 -> (HatP_s (n_p_s, n_q_s), DHatP1_s)."""
+    xi = np.asarray(xi_s)
+    if el_type in (LagrangeElementType.P1, LagrangeElementType.Q1):
+        return 0.5 * np.array([1 - xi, 1 + xi]), np.array([[-0.5], [0.5]])
+    return (np.array([xi * (xi - 1) / 2, xi * (xi + 1) / 2, (xi + 1) * (1 - xi)]), np.array([xi - 0.5, xi + 0.5, -2 * xi]))
+
+
+def _load_device(device):
+    return torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def get_vector_volume(elements, coordinates, f_V_int, hatp, weight, device=None):
+    """Elasticity2D/pythonFEM.py:246-292: vector of volume forces, csc_matrix (2, n_n) like the reference's."""
+    from . import loads
+    dev = _load_device(device)
+    t = lambda a, dt=np.float64: torch.as_tensor(np.ascontiguousarray(np.asarray(a), dtype=dt)).to(dev)  # noqa: E731
+    f = loads.vector_volume(t(elements, np.int64), np.shape(coordinates)[1], t(f_V_int), t(hatp), t(weight).reshape(-1))
+    return ssp.csc_matrix(f.cpu().numpy())
+
+
+def get_vector_traction(elements_s, coordinates, f_t_int, hatp_s, dhatp1_s, wf_s, device=None):
+    """Elasticity2D/pythonFEM.py:295-364: vector of traction forces on the loaded (horizontal) side, csc_matrix (2, n_n)."""
+    from . import loads
+    dev = _load_device(device)
+    t = lambda a, dt=np.float64: torch.as_tensor(np.ascontiguousarray(np.asarray(a), dtype=dt)).to(dev)  # noqa: E731
+    f = loads.vector_traction(t(elements_s, np.int64), t(coordinates), t(f_t_int), t(hatp_s), t(dhatp1_s), t(wf_s))
+    return ssp.csc_matrix(f.cpu().numpy())

@@ -506,3 +506,85 @@ def footing_driver(level=1, et=ElementType.P1, max_steps=1000, mesh=None):
         if zeta_old >= zeta_max or d_zeta < d_zeta_min:
             break
     return {'U': U, 'steps': step, 'trace': trace, 'hist': hist, 'Ep': ep_old}
+
+
+# ---- load vectors of the linear-elastic demo ------------------------------------------------------
+def quadrature_surface(et: ElementType):
+    """(Xi_s (n_q_s,), WF_s (n_q_s,)); Elasticity2D/pythonFEM.py:112-132."""
+    pt = 1 / np.sqrt(3)
+    if et in (ElementType.P1, ElementType.Q1):
+        return np.array([0]), np.array([2])
+    return np.array([-pt, pt]), np.array([1, 1])
+
+
+def local_basis_surface(et: ElementType, xi_s):
+    """(HatP_s (n_p_s,n_q_s), DHatP1_s); Elasticity2D/pythonFEM.py:212-243 (the linear case returns a (2,1) derivative)."""
+    xi = xi_s
+    if et in (ElementType.P1, ElementType.Q1):
+        return 0.5 * np.array([1 - xi, 1 + xi]), np.array([[-0.5], [0.5]])
+    return (np.array([np.multiply(xi, (xi - 1) / 2), np.multiply(xi, (xi + 1) / 2), np.multiply(xi + 1, 1 - xi)]),
+            np.array([xi - 0.5, xi + 0.5, -2 * xi]))
+
+
+def _scatter_in_input_order(vals, nodes, n_n):
+    """What csc_matrix((v, (0, j)), shape=(1, n_n)) does with duplicates: summed per column in input order."""
+    out = np.zeros(n_n)
+    for v, j in zip(vals, nodes.astype(np.int64)):
+        out[j] = out[j] + v
+    return out
+
+
+def vector_volume(elements, coordinates, f_v_int, hatp, weight):
+    """f_V (2, n_n) dense; Elasticity2D/pythonFEM.py:246-292.  Entry (a, g) contributes hatp[a, q] * (weight[g] * f[c, g])
+    to node elements[a, e]; duplicates are summed in the flatten('F') order, i.e. ascending g, then a."""
+    n_n = coordinates.shape[1]
+    n_p, n_e = elements.shape
+    hatphi = np.tile(hatp, (1, n_e))
+    nodes = np.kron(elements, np.ones((1, hatp.shape[1]))).flatten(order='F')
+    out = []
+    for c in range(2):
+        v = np.multiply(hatphi, np.ones((n_p, 1)) * np.multiply(weight, f_v_int[c,])).flatten(order='F')
+        out.append(_scatter_in_input_order(v, nodes, n_n))
+    return np.array(out)
+
+
+def vector_traction(elements_s, coordinates, f_t_int, hatp_s, dhatp1_s, wf_s):
+    """f_t (2, n_n) dense; Elasticity2D/pythonFEM.py:295-364.  The Jacobian uses the x coordinate only (:345) and the load
+    is the LAST integration point's value for every point (f_t_int[c, -1], :356-357) - both kept."""
+    n_n = coordinates.shape[1]
+    n_p_s, n_e_s = elements_s.shape
+    n_q_s = wf_s.shape[0]
+    dhatphi1_s = np.tile(dhatp1_s, (1, n_e_s))
+    hatphi_s = np.tile(hatp_s, (1, n_e_s))
+    coords1 = np.reshape(coordinates[0, elements_s.flatten(order='F').astype(int)], (n_p_s, n_e_s), order='F')
+    coord_int1 = np.kron(coords1, np.ones((1, n_q_s)))
+    j11 = sum(np.multiply(coord_int1, dhatphi1_s))
+    weight_s = np.multiply(abs(j11), np.tile(wf_s, (1, n_e_s)))
+    nodes = np.kron(elements_s, np.ones((1, n_q_s))).flatten(order='F')
+    out = []
+    for c in range(2):
+        v = np.multiply(hatphi_s, np.dot(np.ones((n_p_s, 1)), np.multiply(weight_s, f_t_int[c, -1]))).flatten(order='F')
+        out.append(_scatter_in_input_order(v, nodes, n_n))
+    return np.array(out)
+
+
+def elasticity2d_solve(et: ElementType, elements, coordinates, neumann_nodes, dirichlet_nodes, q_mask, shear, bulk,
+                       volume_force=(0.0, -1.0), traction_force=(0.0, 450.0)):
+    """The linear-elastic demo after mesh generation (Elasticity2D/pythonFEM.py:1100-1171): K, f = f_t + f_V - K u_D with
+    u_D = dirichlet_nodes / 2, dense solve on the free DOFs, stored energy 0.5 u'Ku - (f_t + f_V)'u.  ``elements`` 0-based."""
+    xi, wf = quadrature_volume(et)
+    hatp, d1, d2 = local_basis_volume(et, xi)
+    xs, ws = quadrature_surface(et)
+    hs, ds = local_basis_surface(et, xs)
+    n_int = elements.shape[1] * np.size(wf)
+    K, _, weight, _, _, _ = elastic_stiffness(elements, coordinates, shear * np.ones(n_int), bulk * np.ones(n_int), d1, d2, wf)
+    n_int_s = neumann_nodes.shape[1] * len(ws)
+    f_v = vector_volume(elements, coordinates, np.dot(np.array([volume_force]).T, np.ones((1, n_int))), hatp, weight)
+    f_t = vector_traction(neumann_nodes, coordinates, np.dot(np.array([traction_force]).T, np.ones((1, n_int_s))), hs, ds, ws)
+    load = (f_t + f_v).flatten(order='F')
+    ud = (0.5 * dirichlet_nodes).flatten(order='F')
+    f = load - K @ ud
+    qf = np.asarray(q_mask, dtype=bool).flatten(order='F')
+    u = ud.copy()
+    u[qf] = np.linalg.solve(K.tocsr()[qf][:, qf].toarray(), f[qf])
+    return {"u": u, "energy": 0.5 * u @ (K @ u) - load @ u, "f_V": f_v, "f_t": f_t, "K": K}
