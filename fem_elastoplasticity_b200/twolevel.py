@@ -6,25 +6,58 @@ operator A_c = P^T K P is assembled on the device, inverted once with a dense fa
 applied every iteration by a hand-written dense GEMV.  Any SPD preconditioner yields the same solution as the reference's
 dense LU (Plasticity2D_DP/pythonFEM.py:1062-1066), so parity is unaffected; a matrix that changes between Newton
 iterations (K_tangent) can keep the coarse operator of K_elast."""
-import ctypes as C
-
 import torch
 
 from ._lib import call
 from .plan import _ptr, _stream
 
 
+class CudaTLOps:
+    """The kernels of the C ABI (include/fem_b200.h: fem_coarse_galerkin, fem_tl_*, fem_dense_gemv, fem_pcg_spmv_dot) on
+    one plan.  ``grid`` = (x0, y0, hx, hy, ncx, ncy).  The CPU tests of the host logic inject a NumPy statement of the
+    same steps (tests/test_distributed_cpu.py)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        self.device, self.n_dof, self.n_n, self.coord = plan.device, plan.n_dof, plan.n_n, plan.coord
+
+    def sync(self):
+        torch.cuda.synchronize()
+
+    def jacobi(self, k, mask, out):
+        self.plan.jacobi(k, mask, out=out)
+
+    def galerkin(self, k, row_mask, col_mask, grid, Ac):
+        call("fem_coarse_galerkin", self.plan._h, _ptr(k), _ptr(row_mask), _ptr(col_mask), _ptr(self.coord), *grid, _ptr(Ac), _stream())
+
+    def tl_init(self, rhs, mask, minv, grid, r, rc, scal):
+        call("fem_tl_init", self.n_n, _ptr(rhs), None, _ptr(mask), _ptr(minv), _ptr(self.coord), *grid, _ptr(r), _ptr(rc), _ptr(scal), _stream())
+
+    def gemv(self, n, A, x, y, dot):
+        call("fem_dense_gemv", n, _ptr(A), _ptr(x), _ptr(y), _ptr(dot), _stream())
+
+    def tl_apply(self, mode, r, minv, mask, grid, zc, p, scal, it):
+        call("fem_tl_apply", self.n_n, mode, _ptr(r), _ptr(minv), _ptr(mask), _ptr(self.coord), *grid, _ptr(zc), _ptr(p), _ptr(scal), 0, it, _stream())
+
+    def spmv_dot(self, k, p, q, mask, scal, it):
+        call("fem_pcg_spmv_dot", self.plan._h, _ptr(k), _ptr(p), _ptr(q), _ptr(mask), _ptr(scal), it, _stream())
+
+    def tl_update_xr(self, p, q, minv, grid, x, r, rc, scal, it):
+        call("fem_tl_update_xr", self.n_n, _ptr(p), _ptr(q), _ptr(minv), _ptr(self.coord), *grid, _ptr(x), _ptr(r), _ptr(rc), _ptr(scal), it, _stream())
+
+
 class TwoLevelPCG:
-    def __init__(self, plan, mask, nc=64, part=None, max_coarse_dofs=12000, free_mask=None):
+    def __init__(self, plan, mask, nc=64, part=None, max_coarse_dofs=12000, free_mask=None, ops=None):
         """``mask``: the unknowns of this rank (free DOFs; free AND owned on a strip partition).  ``free_mask``: all free
         DOFs of the local vectors, ghost rows included (needed on a partition: the Galerkin product couples owned rows to
         ghost columns); ``nc``: coarse cells along the shorter side of the bounding box."""
+        self.ops = ops if ops is not None else CudaTLOps(plan)
         self.plan, self.mask, self.part = plan, mask, part
         self.free_mask = free_mask
         if part is not None and part.world > 1 and free_mask is None:
             raise ValueError("TwoLevelPCG on a partition needs free_mask (free DOFs including ghost rows)")
-        dev = plan.device
-        co = plan.coord
+        dev = self.ops.device
+        co = self.ops.coord
         lo = torch.stack([co[0].min(), co[1].min()])
         hi = torch.stack([co[0].max(), co[1].max()])
         if part is not None and part.world > 1:
@@ -38,7 +71,7 @@ class TwoLevelPCG:
             ncx, ncy = max(1, int(ncx * 0.9)), max(1, int(ncy * 0.9))
         self.grid = (float(x0), float(y0), float(lx / ncx), float(ly / ncy), int(ncx), int(ncy))
         self.ncd = 2 * (ncx + 1) * (ncy + 1)
-        n = plan.n_dof
+        n = self.ops.n_dof
         z = lambda m: torch.zeros(m, dtype=torch.float64, device=dev)  # noqa: E731
         self.r, self.p, self.q, self.x, self.minv = (z(n) for _ in range(5))
         self.rc, self.zc, self.scal = z(self.ncd), z(self.ncd), z(8)
@@ -52,11 +85,11 @@ class TwoLevelPCG:
     def setup(self, k_vals):
         """Coarse operator of ``k_vals`` (Galerkin), dense inverse; Jacobi part is refreshed in solve()."""
         import time
-        torch.cuda.synchronize()
+        o = self.ops
+        o.sync()
         t0 = time.perf_counter()
-        P = self.plan
-        Ac = torch.empty((self.ncd, self.ncd), dtype=torch.float64, device=P.device)
-        call("fem_coarse_galerkin", P._h, _ptr(k_vals), _ptr(self.mask), _ptr(self.free_mask), _ptr(P.coord), *self.grid, _ptr(Ac), _stream())
+        Ac = torch.empty((self.ncd, self.ncd), dtype=torch.float64, device=o.device)
+        o.galerkin(k_vals, self.mask, self.free_mask, self.grid, Ac)
         self._reduce(Ac)
         Ac = 0.5 * (Ac + Ac.t())
         d = torch.diagonal(Ac)
@@ -69,7 +102,7 @@ class TwoLevelPCG:
         self.Aci[dead, :] = 0.0
         self.Aci[:, dead] = 0.0
         del Ac, L
-        torch.cuda.synchronize()
+        o.sync()
         self.setup_seconds = time.perf_counter() - t0
         return self
 
@@ -77,36 +110,30 @@ class TwoLevelPCG:
         """z_c = A_c^-1 r_c (replicated on every rank) and the coarse part r_c'z_c of r'z (added once: by rank 0)."""
         self._reduce(self.rc)
         lead = self.part is None or self.part.rank == 0
-        call("fem_dense_gemv", self.ncd, _ptr(self.Aci), _ptr(self.rc), _ptr(self.zc),
-             _ptr(self.scal[rz_slot:rz_slot + 1]) if lead else None, _stream())
+        self.ops.gemv(self.ncd, self.Aci, self.rc, self.zc, self.scal[rz_slot:rz_slot + 1] if lead else None)
 
     def solve(self, k_vals, rhs, rtol=1e-10, maxit=100000, check_every=25, iters=None):
         """Returns (x, iterations, relative residual).  ``iters``: run exactly that many iterations (benchmarks)."""
         if self.Aci is None:
             self.setup(k_vals)
-        P, part, g, s = self.plan, self.part, self.grid, self.scal
-        n_n = P.n_n
-        P.jacobi(k_vals, self.mask, out=self.minv)
+        o, part, g, s = self.ops, self.part, self.grid, self.scal
+        o.jacobi(k_vals, self.mask, self.minv)
         self.x.zero_()
-        call("fem_tl_init", n_n, _ptr(rhs), None, _ptr(self.mask), _ptr(self.minv), _ptr(P.coord), *g, _ptr(self.r), _ptr(self.rc), _ptr(s),
-             _stream())
+        o.tl_init(rhs, self.mask, self.minv, g, self.r, self.rc, s)
         self._coarse_solve(0)                             # z_c, and r_c'z_c into s[0] (rank 0)
         self._reduce(s[0:5])                              # r'z = sum r'D^-1 r + r_c'z_c, r'r, |b|^2
-        call("fem_tl_apply", n_n, 1, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), _ptr(self.p),
-             _ptr(s), 0, 0, _stream())
+        o.tl_apply(1, self.r, self.minv, self.mask, g, self.zc, self.p, s, 0)
         n_it = iters if iters is not None else maxit
         it, rel = 0, float("inf")
         while it < n_it:
             if part is not None:
                 part.halo_exchange(self.p)
-            call("fem_pcg_spmv_dot", P._h, _ptr(k_vals), _ptr(self.p), _ptr(self.q), _ptr(self.mask), _ptr(s), it, _stream())
+            o.spmv_dot(k_vals, self.p, self.q, self.mask, s, it)
             self._reduce(s[3:4])
-            call("fem_tl_update_xr", n_n, _ptr(self.p), _ptr(self.q), _ptr(self.minv), _ptr(P.coord), *g, _ptr(self.x), _ptr(self.r),
-                 _ptr(self.rc), _ptr(s), it, _stream())
+            o.tl_update_xr(self.p, self.q, self.minv, g, self.x, self.r, self.rc, s, it)
             self._coarse_solve(0 if it & 1 else 2)        # + r_c'z_c into the r'z slot: no separate r'z pass
             self._reduce(s[1:3] if it % 2 == 0 else s[0:2])
-            call("fem_tl_apply", n_n, 2, _ptr(self.r), _ptr(self.minv), _ptr(self.mask), _ptr(P.coord), *g, _ptr(self.zc), _ptr(self.p),
-                 _ptr(s), 0, it, _stream())
+            o.tl_apply(2, self.r, self.minv, self.mask, g, self.zc, self.p, s, it)
             it += 1
             if (iters is None and it % check_every == 0) or it == n_it:
                 h = s.cpu()

@@ -140,3 +140,143 @@ def test_partition_bookkeeping():
     assert (owned == 1).all() and n_e == 2 * nx * ny
     with pytest.raises(ValueError):
         StripPartition(4, 10, 0, 3)
+
+
+# ---- two-level PCG: host logic of fem_elastoplasticity_b200.twolevel.TwoLevelPCG under gloo -------------------------
+def _bilinear_prolongation(coord, grid):
+    x0, y0, hx, hy, ncx, ncy = grid
+    fx, fy = (coord[0] - x0) / hx, (coord[1] - y0) / hy
+    cx, cy = np.clip(fx.astype(int), 0, ncx - 1), np.clip(fy.astype(int), 0, ncy - 1)
+    xi, et = np.clip(fx - cx, 0, 1), np.clip(fy - cy, 0, 1)
+    w = [(1 - xi) * (1 - et), xi * (1 - et), xi * et, (1 - xi) * et]
+    base = cx + cy * (ncx + 1)
+    ids = [base, base + 1, base + 1 + (ncx + 1), base + (ncx + 1)]
+    n_n = coord.shape[1]
+    rows = np.concatenate([2 * np.arange(n_n) + c for c in range(2) for _ in range(4)])
+    cols = np.concatenate([2 * ids[k] + c for c in range(2) for k in range(4)])
+    vals = np.concatenate([w[k] for _ in range(2) for k in range(4)])
+    import scipy.sparse as sp
+    return sp.csr_matrix((vals, (rows, cols)), shape=(2 * n_n, 2 * (ncx + 1) * (ncy + 1)))
+
+
+class NumpyTLOps:
+    """Same contract as fem_elastoplasticity_b200.twolevel.CudaTLOps (csrc/twolevel.cu), stated with SciPy on local arrays."""
+
+    def __init__(self, K, coord):
+        self.K, self.n_dof, self.n_n = K.tocsr(), K.shape[0], coord.shape[1]
+        self.coord, self.device, self._np_coord, self._P = torch.as_tensor(coord), torch.device("cpu"), coord, {}
+
+    def P(self, grid):
+        if grid not in self._P:
+            self._P[grid] = _bilinear_prolongation(self._np_coord, grid)
+        return self._P[grid]
+
+    def sync(self):
+        pass
+
+    jacobi = NumpyOps.jacobi
+
+    def galerkin(self, k, row_mask, col_mask, grid, Ac):
+        import scipy.sparse as sp
+        P = self.P(grid)
+        cm = row_mask if col_mask is None else col_mask
+        A = (sp.diags(row_mask.numpy().astype(float)) @ P).T @ self.K @ (sp.diags(cm.numpy().astype(float)) @ P)
+        Ac.copy_(torch.as_tensor(A.toarray()))
+
+    def tl_init(self, rhs, mask, minv, grid, r, rc, scal):
+        scal.zero_()
+        b = rhs * mask
+        r.copy_(b)
+        rc.copy_(torch.as_tensor(self.P(grid).T @ r.numpy()))
+        scal[0], scal[1], scal[4] = torch.dot(r * minv, r), torch.dot(r, r), torch.dot(b, b)
+
+    def gemv(self, n, A, x, y, dot):
+        y.copy_(A @ x)
+        if dot is not None:
+            dot += torch.dot(x, y)
+
+    def tl_apply(self, mode, r, minv, mask, grid, zc, p, scal, it):
+        z = torch.as_tensor(self.P(grid) @ zc.numpy()) * mask + minv * r
+        if mode == 1:
+            p.copy_(z)
+        else:
+            old, new = (2, 0) if it & 1 else (0, 2)
+            beta = scal[new] / scal[old] if scal[old] != 0 else 0.0
+            p.copy_(z + beta * p)
+            scal[3] = 0.0
+
+    spmv_dot = NumpyOps.spmv_dot
+
+    def tl_update_xr(self, p, q, minv, grid, x, r, rc, scal, it):
+        old, new = (2, 0) if it & 1 else (0, 2)
+        alpha = scal[old] / scal[3] if scal[3] != 0 else 0.0
+        x += alpha * p
+        r -= alpha * q
+        scal[1] += torch.dot(r, r)
+        scal[new] += torch.dot(r * minv, r)
+        rc.copy_(torch.as_tensor(self.P(grid).T @ r.numpy()))
+
+
+def _local_problem(part, nx, ny):
+    mesh = part.local_mesh("cpu")
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    elem, coord = mesh["elements"].numpy().astype(np.int64), mesh["coordinates"].numpy()
+    G0, K0 = fo.footing_constants()[:2]
+    n_e = elem.shape[1]
+    K = fo.elastic_stiffness(elem, coord, G0 * np.ones(n_e), K0 * np.ones(n_e), d1, d2, wf)[0]
+    free = mesh["Q"].t().reshape(-1).to(torch.uint8)
+    b_global = np.random.default_rng(5).standard_normal(2 * (nx + 1) * (ny + 1))
+    lo = part.iy0 * part.row_dofs
+    return K, coord, free, torch.as_tensor(b_global[lo:lo + 2 * part.n_n_local].copy()), lo
+
+
+def _tl_worker(rank, world, port, nx, ny, nc, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fem_elastoplasticity_b200.distributed import StripPartition
+    from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+    part = StripPartition(nx, ny, rank, world, size_x=10.0, size_y=27.0)
+    K, coord, free, rhs, lo = _local_problem(part, nx, ny)
+    tl = TwoLevelPCG(None, free & part.owned_mask("cpu"), nc=nc, part=part, free_mask=free, ops=NumpyTLOps(K, coord))
+    x, its, rel = tl.solve(None, rhs, rtol=1e-12, maxit=3000, check_every=1)
+    np.savez(os.path.join(out_dir, f"t{rank}.npz"), x=x.numpy(), lo=lo, its=its, rel=rel, own=np.array(part.owned_dof_range()),
+             grid=np.array(tl.grid))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_strip_partitioned_two_level_pcg_equals_single_domain(tmp_path, world):
+    """TwoLevelPCG's host logic (partitioned Galerkin product with owned rows x free columns, replicated coarse solve,
+    r_c'z_c added by rank 0, placement of the all-reduces) with ranks that have ghost rows on BOTH sides (world 4), on a
+    coarse grid with hx != hy that does not nest in the fine mesh: same iterates as the single-domain run."""
+    from fem_elastoplasticity_b200.distributed import StripPartition
+    from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
+    nx, ny, nc = 10, 24, 3                                     # domain 10 x 27: coarse grid 3 x 8, hx = 3.33, hy = 3.375
+    mp.spawn(_tl_worker, args=(world, _free_port(), nx, ny, nc, str(tmp_path)), nprocs=world, join=True)
+    one = StripPartition(nx, ny, 0, 1, size_x=10.0, size_y=27.0)
+    K, coord, free, rhs, _ = _local_problem(one, nx, ny)
+    tl = TwoLevelPCG(None, free, nc=nc, ops=NumpyTLOps(K, coord))
+    ref, ref_its, ref_rel = tl.solve(None, rhs, rtol=1e-12, maxit=3000, check_every=1)
+    ref = ref.numpy()
+    assert ref_rel <= 1e-12 and tl.grid[2] != tl.grid[3]
+    jac = DistributedPCGJacobiCount(K, free, rhs)
+    assert ref_its < jac                                       # the coarse correction pays even on this small mesh
+    got = np.full_like(ref, np.nan)
+    for r in range(world):
+        d = np.load(tmp_path / f"t{r}.npz")
+        assert np.allclose(d["grid"], np.array(tl.grid))       # every rank lays the same coarse grid over the GLOBAL box
+        assert abs(int(d["its"]) - ref_its) <= 1, (int(d["its"]), ref_its)
+        lo, (a, e) = int(d["lo"]), d["own"]
+        got[lo + a:lo + e] = d["x"][a:e]
+    assert not np.isnan(got).any()
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+
+
+def DistributedPCGJacobiCount(K, free, rhs):
+    from fem_elastoplasticity_b200.distributed import DistributedPCG, StripPartition
+    n_rows = K.shape[0] // 2
+    part = StripPartition(10, n_rows // 11 - 1, 0, 1)
+    pcg = DistributedPCG(None, part, free, ops=NumpyOps(K))
+    return pcg.solve(None, rhs, rtol=1e-12, maxit=20000, check_every=1)[1]
