@@ -280,7 +280,7 @@ def run_gpu(args):
         c_s = time.perf_counter() - c0
         conv = {"preconditioner": f"two-level: Jacobi + {tl.grid[4]}x{tl.grid[5]} bilinear coarse grid ({tl.ncd} coarse DOFs, dense inverse)",
                 "rtol": 1e-10, "iterations": c_its, "relres": c_rel, "seconds": c_s, "ms_per_iteration": 1e3 * c_s / max(c_its, 1),
-                "coarse_setup_seconds": tl.setup_seconds,
+                "coarse_setup_seconds": tl.setup_seconds, "coarse_inverse_residual": tl.inverse_residual,
                 "jacobi_reference": "57 500 iterations / 41.7 s for the footing's elastic solve on the 16M-element mesh, one GPU (tools/full_solve.py)"}
         del tl
     # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned); every step uploads its DS

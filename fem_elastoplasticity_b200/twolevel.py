@@ -77,6 +77,7 @@ class TwoLevelPCG:
         self.rc, self.zc, self.scal = z(self.ncd), z(self.ncd), z(8)
         self.Aci = None
         self.setup_seconds = None
+        self.inverse_residual = None
 
     def _reduce(self, t):
         if self.part is not None:
@@ -101,6 +102,11 @@ class TwoLevelPCG:
         self.Aci = torch.cholesky_inverse(L).contiguous()
         self.Aci[dead, :] = 0.0
         self.Aci[:, dead] = 0.0
+        # self-check of the dense inverse on a few random vectors (set-up only): |A_c A_c^-1 v - v| / |v| on the live DOFs
+        v = torch.randn((self.ncd, 4), dtype=torch.float64, device=o.device) * (~dead).to(torch.float64)[:, None]
+        self.inverse_residual = float(((Ac @ (self.Aci @ v)) - v).norm() / v.norm())
+        if not self.inverse_residual <= 1e-6:
+            raise ArithmeticError(f"two-level PCG: the dense inverse of the coarse operator is inaccurate (residual {self.inverse_residual:.2e})")
         del Ac, L
         o.sync()
         self.setup_seconds = time.perf_counter() - t0
