@@ -7,6 +7,8 @@
 // No atomics, no zero-fill pass, every K value is written exactly once; with -fmad=false the values
 // are bit-identical to the reference.  The 2*deg*2 row accumulators live in warp-private shared
 // memory laid out [entry][lane] (conflict-free), and are written out as contiguous CSR row pairs.
+#include <atomic>
+
 #include "common.cuh"
 
 struct AsmArgs {
@@ -707,6 +709,190 @@ __global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A
   }
 }
 
+// ---- variant E: persistent TMA staging with the row accumulators in warp-private shared memory ---------------------
+// Same staging, slice scheduling and arithmetic as variant D.  D keeps the 4*MAXDEG accumulators of a node in registers
+// and must route every contribution through a `switch` on the (data-dependent) slot; that costs ~160 registers
+// (10 warps/SM) and ~310 executed instructions per incidence.  Here the accumulators live in a warp-private array
+// ps[slot][half][lane] of double2 (conflict-free when the lanes agree on the slot, i.e. on structured meshes), so a
+// contribution is "load 2 x 16 B, 8 adds, store 2 x 16 B" at a computed address: no dispatch, ~70 registers, less
+// than half the instructions.  A thread still owns its node's rows and adds contributions in ascending element order
+// ((acc + p00) + p01 per entry), so the values are bit-identical to variants A-D; the first contribution is added to
+// a zeroed accumulator, which is exact.
+template <int MODE, bool FORCE, int MAXDEG, int BW>
+__global__ void __launch_bounds__(256) assemble_rows_ps_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
+  constexpr int NP = 3;
+  using L = StageLayout<MODE, FORCE>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bw = BW ? BW : A.boxw;
+  constexpr int PS_BYTES = MAXDEG * 2 * 32 * 16;
+  const int warp_bytes = L::warp_b(bw) + PS_BYTES;
+  unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
+  unsigned char* box0 = wbase;
+  unsigned char* box1 = wbase + L::box_b(bw);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * L::box_b(bw));
+  double2* ps = reinterpret_cast<double2*>(wbase + L::warp_b(bw)) + lane;  // ps[(slot*2 + half)*32]
+  const uint32_t bar0 = smem_u32(mbar), bar1 = smem_u32(mbar + 1);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar1), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#pragma unroll
+  for (int j = 0; j < 2 * MAXDEG; ++j) ps[j * 32] = make_double2(0.0, 0.0);
+  __syncwarp();
+  const int64_t n_slices = A.n_slices;
+  auto claim = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(A.slice_counter, 1ULL);
+    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  };
+  int64_t slice = claim();
+  int64_t slice1 = claim();
+  uint32_t ph0 = 0, ph1 = 0;
+  constexpr int CH = 8;
+  struct Book { int nb, st0, st1, deg, width; int64_t base, sbase; };
+  auto load_box = [&](int64_t s, Book& k) {
+    k.nb = 0; k.st0 = 0; k.st1 = 0;
+    if (s < n_slices) { k.nb = A.stage_box[s * 3]; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2]; }
+  };
+  auto load_node = [&](int64_t s, Book& k) {
+    k.deg = 0; k.base = 0;
+    const int64_t a = s * 32 + lane;
+    if (s < n_slices && a < A.n_n) {
+      const int nbp = A.nbr_ptr[a];
+      k.deg = A.nbr_ptr[a + 1] - nbp;
+      k.base = 4 * (int64_t)nbp;
+    }
+  };
+  auto load_sell = [&](int64_t s, Book& k) {
+    k.sbase = 0; k.width = 0;
+    if (s < n_slices) { k.sbase = A.slice_ptr[s]; k.width = (int)((A.slice_ptr[s + 1] - k.sbase) >> 5); }
+  };
+  Book cur, nxt;
+  uint32_t words[CH], nwords[CH];
+  load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
+  load_sell(slice1, nxt);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
+  if (slice < n_slices && lane == 0 && cur.nb >= 1 && cur.nb <= 2) {
+    issue_box<MODE, FORCE>(M, box0, bw, cur.st0, bar0);
+    if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
+  }
+  while (slice < n_slices) {
+    const int64_t next = slice1;
+    const int64_t slice2 = claim();
+    load_box(next, nxt);
+    load_node(next, nxt);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) nwords[i] = (i < nxt.width) ? __ldcs(A.inc_stage + nxt.sbase + (int64_t)i * 32 + lane) : 0u;
+    Book nn;
+    load_sell(slice2, nn);
+    const int nb = cur.nb;
+    const bool staged = nb >= 1 && nb <= 2;
+    const int64_t a = slice * 32 + lane;
+    double f0 = 0.0, f1 = 0.0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (staged) {
+        if (pass == 0) { mbar_wait(bar0, ph0); ph0 ^= 1; }
+        else if (nb == 2) { mbar_wait(bar1, ph1); ph1 ^= 1; }
+      }
+      if (pass == 0 || (staged && nb == 2)) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {  // unrolled: words[i] is a register, no queue rotation
+          const uint32_t word = words[i];
+          const int li = word & 0x1FF;
+          if ((word & 0x80000000u) && !(staged && ((li >= bw) != (pass == 1)))) {
+            const int la = (word >> 9) & 3;
+            PointData<NP, MODE, FORCE> pd;
+            if (staged) {
+              const int o = li - pass * bw;
+              const unsigned char* bb = pass ? box1 : box0;
+              const double* g = reinterpret_cast<const double*>(bb) + o;
+              pd.w = g[0];
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                pd.d1[p] = g[(1 + p) * bw];
+                pd.d2[p] = g[(4 + p) * bw];
+              }
+              bb += L::geom_b(bw);
+              const double* t0 = reinterpret_cast<const double*>(bb) + o;
+              if (MODE == MODE_ELASTIC) {
+                pd.raw[0] = t0[0];
+                pd.raw[1] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+              } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) pd.raw[k] = t0[k * bw];
+                if (MODE == MODE_TANGENT_REF) {
+                  pd.raw[MODE == MODE_TANGENT_REF ? 9 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+                  pd.raw[MODE == MODE_TANGENT_REF ? 10 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw)) + o)[0];
+                }
+              }
+              if (FORCE) {
+                const double* sp = reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw) + L::t2_b(bw)) + o;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pd.s[k] = sp[k * bw];
+              }
+            } else {  // direct loads (slices with more than two boxes)
+              const uint32_t key = A.inc_key[cur.sbase + (int64_t)i * 32 + lane];
+              load_point<NP, MODE, FORCE>(A, (int64_t)(key >> 3), pd);
+            }
+            double tx[3], ty[3];
+            point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
+#pragma unroll
+            for (int lb = 0; lb < NP; ++lb) {
+              const int slot = (word >> (11 + 4 * lb)) & 15;
+              double2* r = ps + slot * 64;
+              const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+              double2 v0 = r[0], v1 = r[32];
+              v0.x = (v0.x + tx[0] * b1) + tx[2] * b2;  // K[2a  , 2b  ]
+              v0.y = (v0.y + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
+              v1.x = (v1.x + ty[0] * b1) + ty[2] * b2;  // K[2a+1, 2b  ]
+              v1.y = (v1.y + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+              r[0] = v0;
+              r[32] = v1;
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane is done reading this pass's box: it may be overwritten by the next slice's copy
+      if (lane == 0 && nxt.nb >= 1 && nxt.nb <= 2) {
+        if (pass == 0) issue_box<MODE, FORCE>(M, box0, bw, nxt.st0, bar0);
+        else if (nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
+      }
+    }
+    {
+      const int deg = (a < A.n_n) ? cur.deg : 0;
+      if (FORCE && a < A.n_n) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+      double2* row0 = reinterpret_cast<double2*>(A.K_vals + cur.base);
+      double2* row1 = row0 + deg;
+#pragma unroll
+      for (int j = 0; j < MAXDEG; ++j) {
+        if (j < deg) {
+          double2 v0 = ps[j * 64], v1 = ps[j * 64 + 32];
+          if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction
+            const double2 k0 = reinterpret_cast<const double2*>(A.Kel + cur.base)[j];
+            const double2 k1 = reinterpret_cast<const double2*>(A.Kel + cur.base)[deg + j];
+            v0.x = k0.x + v0.x; v0.y = k0.y + v0.y; v1.x = k1.x + v1.x; v1.y = k1.y + v1.y;
+          }
+          __stcs(row0 + j, v0);
+          __stcs(row1 + j, v1);
+          ps[j * 64] = make_double2(0.0, 0.0);  // ready for the next slice
+          ps[j * 64 + 32] = make_double2(0.0, 0.0);
+        }
+      }
+    }
+    slice = next;
+    slice1 = slice2;
+    cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
+    cur.sbase = nxt.sbase; cur.width = nxt.width;
+    nxt.sbase = nn.sbase; nxt.width = nn.width;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) words[i] = nwords[i];
+  }
+}
+
 template <int MODE, bool FORCE>
 static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   using L = StageLayout<MODE, FORCE>;
@@ -738,18 +924,22 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A, M);
-  } else {                                   // persistent, software-pipelined
-    void (*kern)(const AsmArgs, const StageMaps) = (bw == 66) ? assemble_rows_tmap_kernel<MODE, FORCE, 8, 66>
-                                                               : assemble_rows_tmap_kernel<MODE, FORCE, 8, 0>;
-    // warps per CTA (4..6) that packs the most warps into the 227 KB of an SM (1 KB per CTA is reserved)
+  } else {                                   // persistent, software-pipelined: D (register accumulators) or E (shared-memory accumulators)
+    const bool ps = g_fem_tuning.assemble_variant != 6;  // E unless D is asked for
+    void (*kern)(const AsmArgs, const StageMaps) =
+        ps ? ((bw == 66) ? assemble_rows_ps_kernel<MODE, FORCE, 8, 66> : assemble_rows_ps_kernel<MODE, FORCE, 8, 0>)
+           : ((bw == 66) ? assemble_rows_tmap_kernel<MODE, FORCE, 8, 66> : assemble_rows_tmap_kernel<MODE, FORCE, 8, 0>);
+    const size_t per_warp = (size_t)L::warp_b(bw) + (ps ? 8 * 2 * 32 * 16 : 0);
+    // warps per CTA that packs the most warps into the 227 KB of an SM (1 KB per CTA is reserved)
     int best = 0;
-    for (int w = 4; w <= 6; ++w) {
-      const size_t sm = (size_t)w * L::warp_b(bw);
+    for (int w = (ps ? 1 : 4); w <= (ps ? 8 : 6); ++w) {
+      const size_t sm = (size_t)w * per_warp;
       const int per = (int)((227 * 1024) / (sm + 1024));
-      if (per * w > best) { best = per * w; warps = w; }
+      if (per * w >= best) { best = per * w; warps = w; }
     }
-    if (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= 6) warps = g_fem_tuning.assemble_warps;
-    smem = (size_t)warps * L::warp_b(bw);
+    if (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= (ps ? 8 : 6)) warps = g_fem_tuning.assemble_warps;
+    smem = (size_t)warps * per_warp;
+    if (smem > 227 * 1024) return -1;
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -757,9 +947,10 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     int64_t blocks = (int64_t)per_sm * P->sm_count;
     const int64_t need = fem_div_up(P->n_slices, warps);
     if (blocks > need) blocks = need;
-    // one of 8 counters, round-robin per launch, so launches of the same plan on different streams never share one
-    static unsigned launch_no = 0;
-    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8) + (launch_no++ & 7u);
+    // one of FEM_SLICE_COUNTERS counters of this plan, round-robin per launch (atomic: host threads may launch concurrently),
+    // so up to FEM_SLICE_COUNTERS launches of one plan may be in flight on different streams without sharing a counter
+    static std::atomic<unsigned> launch_no{0};
+    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8) + (launch_no.fetch_add(1u) % FEM_SLICE_COUNTERS);
     FEM_CUDA_CHECK(cudaMemsetAsync(A.slice_counter, 0, sizeof(unsigned long long), st));
     kern<<<(unsigned)blocks, warps * 32, smem, st>>>(A, M);
   }
@@ -808,7 +999,7 @@ static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   const int variant = g_fem_tuning.assemble_variant;
   // measured defaults (tools/tune.py, 16M elements): elastic -> one-shot TMA, tangent(+force) -> persistent pipelined TMA,
   // reference-order tangent (reads K_elast in its write-out) -> register kernel
-  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && MODE != MODE_TANGENT_REF) || (variant == 6 || variant == 7))) {
+  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && MODE != MODE_TANGENT_REF) || (variant == 6 || variant == 7 || variant == 8))) {
     const int rc = launch_assemble_tma<MODE == MODE_FORCE_ONLY ? MODE_TANGENT : MODE, FORCE>(P, A, st);
     if (rc >= 0) return rc;  // -1: inputs not 16-byte aligned / too much shared memory -> register kernel
   }

@@ -14,6 +14,7 @@
 #define FEM_MAX_NQ 9
 #define FEM_WARP 32
 #define FEM_INVALID_KEY 0xFFFFFFFFu
+#define FEM_SLICE_COUNTERS 64  // dynamic-scheduler counters per plan (dscratch[8 .. 8 + FEM_SLICE_COUNTERS))
 #define FEM_STAGE_MAXBOXW 96   // widest TMA box (elements); longer runs are split
 // 2-D tensor map over `rows` SoA rows of n_int doubles (row stride n_int), box = rows x boxw
 int fem_encode_rows_map(CUtensorMap* out, const double* base, int64_t n_int, int rows, int boxw);
@@ -25,7 +26,7 @@ struct FemTuning {
   int assemble_warps;      // warps per block of the assembly kernel (0 = 4)
   int spmv_group;          // lanes per node in the SpMV (0 = by degree)
   int spmv_blocks_per_sm;  // 0 = 32
-  int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D)
+  int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D), 8 persistent TMA with shared-memory accumulators (E)
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
   int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
 };
@@ -79,7 +80,7 @@ struct fem_plan {
   double* dphi2;   // [n_p][n_int]
   double* weight;  // [n_int]
   // scratch
-  double* dscratch;  // small device scratch (8 doubles)
+  double* dscratch;  // small device scratch: 8 doubles (PCG scalars) + FEM_SLICE_COUNTERS 8-byte counters
   // TMA staging data of the P1 assembly kernel (valid when stage_ok): per 32-node slice the touched elements as
   // <= FEM_STAGE_RMAX runs of consecutive ids (16-byte aligned), and per incidence its position in the staged buffer
   int stage_ok, stage_boxw;

@@ -588,7 +588,7 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     P->weight = P->geom;
     P->dphi1 = P->geom + P->n_int;
     P->dphi2 = P->geom + (int64_t)(1 + n_p) * P->n_int;
-    if ((rc = dmalloc(P, &P->dscratch, 16)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->dscratch, 8 + FEM_SLICE_COUNTERS)) != FEM_OK) break;
     if ((rc = launch_geometry(P, coord, flags + 3, st)) != FEM_OK) break;
     // TMA staging plan (P1 meshes of bounded valence whose slices touch few runs of consecutive elements)
     P->stage_ok = 0;

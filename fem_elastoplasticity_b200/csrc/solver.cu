@@ -192,10 +192,17 @@ static unsigned vec_grid(const int64_t n_items, const int sm_count) {
   if (b < 1) b = 1;
   return (unsigned)b;
 }
-static int sm_count_now() {
-  int dev = 0, sms = 148;
+static int sm_count_now() {  // cached per device: one attribute query per device and process, not per launch
+  static int cache[64] = {0};
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 0 || dev >= 64) return 148;
+  int sms = cache[dev];
+  if (sms == 0) {
+    sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = sms;
+  }
   return sms;
 }
 

@@ -52,7 +52,7 @@ def main():
     r = dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm)
     kel_ref = None
     k, F = P.empty(P.nnz), P.empty(P.n_dof)
-    for v, name in ((2, "reg"), (7, "tma"), (6, "tmapipe"), (0, "default")):
+    for v, name in ((2, "reg"), (7, "tma"), (6, "tmapipe"), (8, "ps"), (0, "default")):
         knob("assemble_variant", v)
         res[f"assemble_elastic_{name}_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
         kel = k.clone()
@@ -64,6 +64,11 @@ def main():
             kel_ref, kt_ref, F_ref = kel, kt, F.clone()
         else:
             res[f"{name}_equals_reg_bits"] = bool(torch.equal(kel, kel_ref) and torch.equal(kt, kt_ref) and torch.equal(F, F_ref))
+    for w in (1, 2, 3, 4, 8):                        # warps per CTA of the persistent shared-memory-accumulator kernel (E)
+        knob("assemble_variant", 8), knob("assemble_warps", w)
+        res[f"assemble_tangent_force_ps_w{w}_ms"] = timeit(lambda: P.assemble_tangent_force(r["ds"], r["s"], out_k=k, out_f=F))
+        res[f"assemble_elastic_ps_w{w}_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
+    knob("assemble_warps", 0)
     knob("assemble_variant", 0)
     res["internal_force_ms"] = timeit(lambda: P.internal_force(r["s"], out=F))
     u = torch.randn(P.n_dof, dtype=torch.float64, device="cuda")
