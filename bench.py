@@ -152,6 +152,129 @@ def run_reference(args):
     emit(line)
 
 
+def multi_gpu_checks(args, P, part, mesh, pcg, k_tan, rhs, rm, d1, d2, wf, dev):
+    """Correctness carried by an N > 1 run itself (every rank raises on failure):
+    (a) the ghost cell row of rank r holds the same tangent operators as the first owned cell row of rank r+1;
+    (b) the owned interface rows of K_tangent equal, bit for bit, a stand-alone single-GPU assembly of the two cell rows
+        around the interface (same cells, same data, no partition);
+    (c) the partitioned matrix is symmetric as ONE global operator: y'(K x) == x'(K y) over all ranks;
+    (d) the fused iteration (exchanges inside the kernels over NVLink peer memory) reproduces the NCCL variant: same r'r
+        after the step's fixed number of iterations."""
+    import torch
+    import torch.distributed as dist
+    from fem_elastoplasticity_b200 import distributed as fdist, meshgen
+    from fem_elastoplasticity_b200.plan import FemPlan
+    nx, world, rank = part.nx, part.world, part.rank
+    out = {}
+    ds = rm["ds"]
+    row = 2 * nx                                                     # elements per cell row
+    # (a) checksums of the shared cell rows
+    sums = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+    sums[2 * rank] = ds[:, :row].sum()                               # first owned cell row (local cell row 0)
+    if part.has_upper:
+        sums[2 * rank + 1] = ds[:, part.ny_loc * row:(part.ny_loc + 1) * row].sum()    # ghost cell row
+    dist.all_reduce(sums)
+    h = sums.cpu().numpy()
+    for r in range(world - 1):
+        assert h[2 * r + 1] == h[2 * (r + 1)], f"ghost cell row of rank {r} differs from the owner's data"
+    out["ghost_data_identical"] = True
+    # (b) stand-alone assembly of the cell rows around the upper interface (rank 0 also checks its lower boundary rows)
+    if part.has_upper:
+        lo_cell = part.ny_loc - 1
+        thin = meshgen.square_mesh_p1(nx, 2, part.size_x, part.size_y, device=dev, iy0=part.iy0 + lo_cell, n_y_global=part.ny_global,
+                                      size_y_global=part.size_y)
+        Pt = FemPlan(thin["elements"], thin["coordinates"], d1, d2, wf, device=dev)
+        kt = Pt.assemble_tangent(ds[:, lo_cell * row:(lo_cell + 2) * row].contiguous())
+        a0, a1 = int(Pt.row_ptr[2 * (nx + 1)]), int(Pt.row_ptr[4 * (nx + 1)])          # middle node row of the thin mesh
+        n0 = part.ny_loc * (nx + 1)                                                    # the same nodes in the local mesh: top owned row
+        b0, b1 = int(P.row_ptr[2 * n0]), int(P.row_ptr[2 * (n0 + nx + 1)])
+        assert a1 - a0 == b1 - b0 and torch.equal(kt[a0:a1], k_tan[b0:b1]), "interface rows differ from the stand-alone assembly"
+        del Pt, kt
+    out["interface_rows_equal_standalone_assembly"] = True
+    # (c) global symmetry
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = torch.randn(P.n_dof, dtype=torch.float64, device=dev, generator=g)
+    ys = torch.randn(P.n_dof, dtype=torch.float64, device=dev, generator=g)
+    part.halo_exchange(xs, ys)
+    own = part.owned_mask(dev)
+    kx, ky = P.spmv(k_tan, xs, mask=own), P.spmv(k_tan, ys, mask=own)
+    sy = torch.stack([torch.dot(ys, kx), torch.dot(xs, ky)])
+    dist.all_reduce(sy)
+    asym = abs(float(sy[0] - sy[1])) / abs(float(sy[0]))
+    assert asym <= 1e-11, f"partitioned K_tangent is not symmetric: {asym:.2e}"
+    out["global_symmetry_rel"] = asym
+    # (d) fused vs NCCL iteration
+    if getattr(pcg, "fused", False):
+        ref = fdist.DistributedPCG(P, part, pcg.mask, peer=False, use_graph=False)
+        ref.solve(k_tan, rhs, iters=args.pcg_iters)
+        rr_ref = float(ref.scal[1].item())
+        pcg.solve(k_tan, rhs, iters=args.pcg_iters)
+        rr_fused = float(pcg.peer.comm.view(torch.float64)[pcg.WORD_OUT + 1].item())
+        xd = torch.stack([(pcg.x - ref.x).abs().max(), ref.x.abs().max()])
+        dist.all_reduce(xd, op=dist.ReduceOp.MAX)
+        out["fused_vs_nccl_rr_rel"] = abs(rr_fused - rr_ref) / abs(rr_ref)
+        out["fused_vs_nccl_x_rel"] = float(xd[0] / xd[1])
+        assert out["fused_vs_nccl_rr_rel"] <= 1e-8 and out["fused_vs_nccl_x_rel"] <= 1e-8, out
+        del ref
+    return out
+
+
+def strong_scaling_part(args, world, rank, dev, d1, d2, wf, pcg_one_gpu_ms=None):
+    """The nx x nx mesh of config 4 split over the N GPUs (strong scaling), timed in the same run as the weak-scaling
+    headline: step ms and PCG ms/iteration, max over ranks.  The one-GPU time of the same mesh is the N = 1 run's."""
+    import torch
+    import torch.distributed as dist
+    from fem_elastoplasticity_b200 import distributed as fdist, meshgen
+    from fem_elastoplasticity_b200.plan import FemPlan, axpby, dp_return_map
+    nx = args.nx
+    ny_global = -(-nx // world) * world
+    part = fdist.StripPartition(nx, ny_global, rank, world, size_x=10.0, size_y=10.0 * ny_global / nx)
+    mesh = part.local_mesh(dev)
+    P = FemPlan(mesh["elements"], mesh["coordinates"], d1, d2, wf, device=dev)
+    G, Kb, eta, c = meshgen.footing_materials(P.n_int, dev)
+    Es = meshgen.synthetic_strain_global(P.n_int, 2 * nx * part.iy0, dev)
+    u = meshgen.synthetic_nodal_global(P.n_n, (nx + 1) * part.iy0, dev)
+    mask = part.free_owned_mask(P, mesh)
+    ep_old = torch.zeros((4, P.n_int), dtype=torch.float64, device=dev)
+    E, k_tan, F, rhs, rm = P.empty(3, P.n_int), P.empty(P.nnz), P.empty(P.n_dof), P.empty(P.n_dof), {}
+    k_el = P.assemble_elastic(G, Kb)
+    pcg = fdist.DistributedPCG(P, part, mask, peer={"auto": "auto", "nccl": False, "peer": True, "fused": "fused"}[args.halo], use_graph=not args.no_graph)
+    evs = []
+
+    def step(rec):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        P.strain(u, out=E)
+        dp_return_map(Es, ep_old, G, Kb, eta, c, want_ep=False, out=rm)
+        P.assemble_tangent_force(rm["ds"], rm["s"], out_k=k_tan, out_f=F)
+        axpby(-1.0, F, 0.0, F, out=rhs)
+        e[1].record()
+        x, _ = pcg.solve(k_tan, rhs, iters=args.pcg_iters)
+        e[2].record()
+        pcg.energy_norms(k_el, x, u, rhs)
+        if rec:
+            evs.append(e)
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    n_steps = max(5, min(args.steps, 20))
+    for _ in range(n_steps):
+        step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    v = torch.tensor([t0.elapsed_time(t1) / n_steps, float(np.mean([e[1].elapsed_time(e[2]) for e in evs])) / max(args.pcg_iters, 1)],
+                     dtype=torch.float64, device=dev)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return {"strong_n_elements": 2 * nx * ny_global, "strong_step_ms": float(v[0]), "strong_pcg_ms_per_iter": float(v[1]),
+            "strong_note": f"config 4 mesh ({nx}x{ny_global} cells) split over {world} GPUs, same step and PCG iteration count as the headline; "
+                           "the one-GPU time of this mesh is ms_per_step of the N=1 run"}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
@@ -190,8 +313,11 @@ def run_gpu(args):
     t_plan = time.perf_counter() - t_plan0
     n_e_owned = part.n_e_owned
     G, Kb, eta, c = meshgen.footing_materials(P.n_int, dev)
-    Es = meshgen.synthetic_strain(P.n_int, dev, seed=rank)
-    u = 1e-3 * torch.randn(P.n_dof, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(100 + rank))
+    # synthetic state as a function of the GLOBAL element / node id: the ghost cell row a rank keeps carries its owner's
+    # values, so the ranks' owned rows form ONE symmetric global matrix (per-rank seeds made K unsymmetric across the
+    # interfaces in round 1 - the reason its partitioned converged solve stalled)
+    Es = meshgen.synthetic_strain_global(P.n_int, 2 * nx * part.iy0, dev)
+    u = meshgen.synthetic_nodal_global(P.n_n, (nx + 1) * part.iy0, dev)
     mask = part.free_owned_mask(P, mesh)
     E = P.empty(3, P.n_int)
     ep_old = torch.zeros((4, P.n_int), dtype=torch.float64, device=dev)
@@ -263,26 +389,42 @@ def run_gpu(args):
         return b0.elapsed_time(b1) / reps
     t_tan_only = iso(lambda: P.assemble_tangent(rm["ds"], out=k_tan))
     t_el_only = iso(lambda: P.assemble_elastic(G, Kb, out=k_el))
-    # ---- one CONVERGED inner solve (rtol 1e-10) of the step's system with the two-level preconditioner.  Default on one
-    # GPU only; --converged-solve forces it on N > 1 ranks (coarse operator all-reduced and replicated, NCCL exchanges):
-    # verified at 2 GPUs (same iteration count as one GPU), but the one 8-GPU weak-scaling attempt (25x218 coarse grid,
-    # 128M elements) did not converge within 50 000 iterations and is an open item
+    # ---- correctness carried by the run itself (N > 1): see multi_gpu_checks
+    checks = multi_gpu_checks(args, P, part, mesh, pcg, k_tan, rhs, rm, d1, d2, wf, dev) if world > 1 else None
+    # ---- one CONVERGED inner solve (rtol 1e-10) of the step's system with the two-level preconditioner, at every N
+    # (coarse operator all-reduced and replicated, NCCL exchanges).  A solve that does not reach rtol is reported as such.
     conv = None
-    if not args.no_converged_solve and (world == 1 or args.converged_solve):
+    if not args.no_converged_solve:
+        from fem_elastoplasticity_b200.distributed import PCGNotConverged
         from fem_elastoplasticity_b200.twolevel import TwoLevelPCG
         tl = TwoLevelPCG(P, mask, nc=args.coarse_cells, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"])).setup(k_el)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         c0 = time.perf_counter()
-        _, c_its, c_rel = tl.solve(k_tan, rhs, rtol=1e-10, maxit=20000, check_every=50)
+        converged = True
+        try:
+            _, c_its, c_rel = tl.solve(k_tan, rhs, rtol=1e-10, maxit=args.converged_maxit, check_every=50)
+        except PCGNotConverged as e:
+            converged, c_its, c_rel = False, e.iters, e.relres
         torch.cuda.synchronize()
         c_s = time.perf_counter() - c0
+        # true residual of the returned iterate (not the recurrence): |mask (b - K x)| / |mask b| over all ranks
+        kx = P.spmv(k_tan, tl.x, mask=mask)
+        tr = torch.stack([((rhs - kx) * mask).square().sum(), (rhs * mask).square().sum()])
+        if world > 1:
+            dist.all_reduce(tr)
+        true_rel = float((tr[0] / tr[1]).sqrt().item())
         conv = {"preconditioner": f"two-level: Jacobi + {tl.grid[4]}x{tl.grid[5]} bilinear coarse grid ({tl.ncd} coarse DOFs, dense inverse)",
-                "rtol": 1e-10, "iterations": c_its, "relres": c_rel, "seconds": c_s, "ms_per_iteration": 1e3 * c_s / max(c_its, 1),
+                "converged": converged, "rtol": 1e-10, "iterations": c_its, "relres": c_rel, "true_relres": true_rel, "seconds": c_s,
+                "ms_per_iteration": 1e3 * c_s / max(c_its, 1),
                 "coarse_setup_seconds": tl.setup_seconds, "coarse_inverse_residual": tl.inverse_residual,
                 "jacobi_reference": "57 500 iterations / 41.7 s for the footing's elastic solve on the 16M-element mesh, one GPU (tools/full_solve.py)"}
+        if converged:
+            assert true_rel <= 1e-8, f"converged solve: true residual {true_rel:.2e}"
         del tl
+    # ---- strong scaling in the same run (N > 1): the nx x nx mesh of config 4 split over the N GPUs, same step
+    strong = strong_scaling_part(args, world, rank, dev, d1, d2, wf, pcg_one_gpu_ms=None) if (world > 1 and args.scaling == "weak" and not args.no_strong) else None
     # ---- end-to-end leg: tangent assembly through the public API with HOST buffers (pinned); every step uploads its DS
     # (H2D) and downloads its K values (D2H) inside the timed region.  Two steps are in flight on two streams with
     # double-buffered device arrays, so the upload of step i+1 overlaps the download of step i (PCIe is full duplex).
@@ -370,9 +512,10 @@ def run_gpu(args):
                   "pcg_newton_s_per_step": ms_step * 1e-3, "pcg_ms_per_iter": pcg_ms_iter, "strain_ms": t_strain, "criterion_ms": t_crit,
                   "assembly_ms": t_asm, "return_map_ms": t_rm, "tangent_only_isolated_ms": t_tan_only,
                   "tangent_only_isolated_melem_s": n_e_tot / (t_tan_only * 1e-3) / 1e6,
-                  "elastic_isolated_melem_s": n_e_tot / (t_el_only * 1e-3) / 1e6, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6},
-        "pcg_converged_solve": conv,
-        "newton_step_converged_s": (None if conv is None else (t_strain + t_rm + t_asm + t_crit) * 1e-3 + conv["seconds"]),
+                  "elastic_isolated_melem_s": n_e_tot / (t_el_only * 1e-3) / 1e6, "newton_step_melem_s": n_e_tot / (ms_step * 1e-3) / 1e6,
+                  **({} if strong is None else dict(strong, strong_speedup_vs_weak_step=ms_step / strong["strong_step_ms"]))},
+        "pcg_converged_solve": conv, "multi_gpu_checks": checks,
+        "newton_step_converged_s": (None if (conv is None or not conv["converged"]) else (t_strain + t_rm + t_asm + t_crit) * 1e-3 + conv["seconds"]),
         "roofline": roof, "rooflines": rooflines, "clocks": clocks,
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent: pinned host DS -> device -> kernel -> pinned host K values, every step; two steps in flight "
@@ -419,8 +562,10 @@ def main():
                     help="weak: nx x nx cells per GPU (config 5 at 8 GPUs); strong: one nx x nx mesh split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-converged-solve", action="store_true", help="skip the converged two-level PCG solve reported beside the fixed-iteration step")
-    ap.add_argument("--converged-solve", action="store_true", help="also run the converged two-level solve on N > 1 GPUs (default: one GPU only)")
+    ap.add_argument("--converged-solve", action="store_true", help="(kept for compatibility: the converged solve now runs at every N)")
     ap.add_argument("--coarse-cells", type=int, default=64)
+    ap.add_argument("--converged-maxit", type=int, default=8000, help="iteration cap of the converged two-level solve")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling part of an N > 1 run")
     ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "peer", "fused"], help="multi-GPU exchanges of the PCG: fused = inside the kernels over NVLink peer memory; auto = fused, NCCL if symmetric memory is unavailable")
     ap.add_argument("--no-graph", action="store_true", help="launch the PCG iterations eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -15,6 +15,10 @@
 #define FEM_WARP 32
 #define FEM_INVALID_KEY 0xFFFFFFFFu
 #define FEM_SLICE_COUNTERS 64  // dynamic-scheduler counters per plan (dscratch[8 .. 8 + FEM_SLICE_COUNTERS))
+#define FEM_SPMV_TILE 128      // nodes (row pairs) per SpMV tile
+#define FEM_SPMV_MAXSEG 4      // contiguous column ranges per tile
+#define FEM_SPMV_CAP 512       // staged x entries (nodes) per tile: 8 KB of shared memory per buffer
+#define FEM_SPMV_DESC 12       // int32 words per tile descriptor
 #define FEM_STAGE_MAXBOXW 96   // widest TMA box (elements); longer runs are split
 // 2-D tensor map over `rows` SoA rows of n_int doubles (row stride n_int), box = rows x boxw
 int fem_encode_rows_map(CUtensorMap* out, const double* base, int64_t n_int, int rows, int boxw);
@@ -28,6 +32,8 @@ struct FemTuning {
   int spmv_blocks_per_sm;  // 0 = 32
   int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D), 8 persistent TMA with shared-memory accumulators (E)
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
+  int spmv_staged;         // 0 auto (staged x when the plan has tiles), 1 gather x from global memory (round-1 kernel)
+  int peer_timeout_ms;     // bound of the in-kernel waits of the fused multi-GPU PCG (0 = 10 000 ms)
   int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
 };
 extern FemTuning g_fem_tuning;
@@ -89,6 +95,13 @@ struct fem_plan {
   uint32_t* inc_stage;   // [sell_entries]: li | la<<9 | slot0<<11 | slot1<<15 | slot2<<19 | valid<<31, li = box*boxw + offset
   double* geom;          // one allocation [1 + 2*n_p][n_int]: weight, dphi1 rows, dphi2 rows (one TMA box brings all rows)
   CUtensorMap geom_map;
+  // x-staging plan of the SpMV (spmv.cuh): per tile of FEM_SPMV_TILE consecutive nodes the referenced columns as
+  // <= FEM_SPMV_MAXSEG contiguous node ranges (brought into shared memory by bulk async copies), and per 2x2 block the
+  // position of its column inside that staged buffer
+  int64_t n_tiles;
+  int32_t* tile_seg;   // [n_tiles][FEM_SPMV_DESC]: nseg (0 = gather from global), total nodes, then (start, len) per segment
+  uint16_t* nbr_loc;   // [n_blocks]
+  int64_t spmv_fallback_tiles;
   int64_t bytes;
 };
 

@@ -17,7 +17,7 @@
 // neighbour's flag word - issued by the few blocks that own those rows, which run FIRST in kernel C, so the flag is
 // long there when the neighbour's next SpMV starts.  Partials are summed by every rank in rank order, so all ranks
 // compute bit-identical alpha and beta.  The sequence number is a device-resident iteration counter that only ever
-// grows, so a graph replay needs no changing arguments.  Waits are bounded (2 s): on a time-out the kernel sets an
+// grows, so a graph replay needs no changing arguments.  Waits are bounded (10 s, "peer_timeout_ms"): on a time-out the kernel sets an
 // error word and carries on, so a dead peer cannot hang the GPU.
 //
 // Why overwriting is safe: rank X publishes p'q(it) at the end of A(it), i.e. after it passed the wait of C(it-1), which
@@ -49,6 +49,7 @@ struct PeerView {
   uint64_t* peer[FEM_PEER_MAX];  // peer[r] = rank r's block (peer[rank] == local)
   int rank, world;
   int nowait;  // diagnostic: never spin (see FemTuning::peer_nowait)
+  uint64_t timeout_ns;  // bound of every wait ("peer_timeout_ms" tuning key, default 10 s)
 };
 
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
@@ -65,15 +66,14 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
-#define FEM_PEER_TIMEOUT_NS 2000000000ull
 
 // Poll a flag in this rank's own block until a peer has stored a sequence number >= want.
-__device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want, uint64_t* err, const int nowait) {
+__device__ __noinline__ void wait_flag(const uint64_t* flag, const uint64_t want, uint64_t* err, const int nowait, const uint64_t timeout_ns) {
   if (ld_acquire_sys(flag) >= want || nowait) return;
   if (*reinterpret_cast<volatile uint64_t*>(err)) return;  // an earlier wait already failed: do not stall again
   const uint64_t t0 = global_timer_ns();
   while (ld_acquire_sys(flag) < want) {
-    if (global_timer_ns() - t0 > FEM_PEER_TIMEOUT_NS) {
+    if (global_timer_ns() - t0 > timeout_ns) {
       atomicExch(reinterpret_cast<unsigned long long*>(err), 1ull);
       return;
     }
@@ -93,13 +93,13 @@ __device__ __forceinline__ bool line_try(const uint64_t* line, const uint32_t se
   *v = __longlong_as_double((long long)(((uint64_t)hi << 32) | lo));
   return f0 == seq && f1 == seq;
 }
-__device__ __noinline__ double line_wait(const uint64_t* line, const uint32_t seq, uint64_t* err, const int nowait) {
+__device__ __noinline__ double line_wait(const uint64_t* line, const uint32_t seq, uint64_t* err, const int nowait, const uint64_t timeout_ns) {
   double v;
   if (line_try(line, seq, &v) || nowait) return v;
   if (*reinterpret_cast<volatile uint64_t*>(err)) return 0.0;
   const uint64_t t0 = global_timer_ns();
   while (!line_try(line, seq, &v)) {
-    if (global_timer_ns() - t0 > FEM_PEER_TIMEOUT_NS) {
+    if (global_timer_ns() - t0 > timeout_ns) {
       atomicExch(reinterpret_cast<unsigned long long*>(err), 1ull);
       return 0.0;
     }
@@ -123,20 +123,25 @@ __device__ __forceinline__ bool arrive_last(uint64_t* ticket_word, const unsigne
 }
 
 // ---- A: q = K p and the partial p'q ---------------------------------------------------------------------------------
-template <int GROUP, int U>
-__global__ void __launch_bounds__(256) ppcg_spmv_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
-                                                        const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
-                                                        const double* __restrict__ p, double* __restrict__ q,
+// p is NOT const/__restrict__ and is never read through the non-coherent path: its ghost rows are stored by the
+// neighbour GPUs while this kernel is already resident (it spins on the halo flags), so every load of p is a coherent
+// one (bulk async copies after a proxy fence, or ld.global.cg in the gather fallback).
+template <int GROUP>
+__global__ void __launch_bounds__(256) ppcg_spmv_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+                                                        const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
+                                                        const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
+                                                        const double* p, double* __restrict__ q,
                                                         const uint8_t* __restrict__ mask, const PeerView pv) {
   __shared__ double red[32];
   __shared__ int sh_last;
+  __shared__ SpmvTileSmem sm;
   uint64_t* L = pv.local;
   const uint64_t it = L[PW_IT];
   // ghost rows of p: stored by the neighbours' C(it-1); nothing of p is loaded before the flags are seen
-  if (threadIdx.x == 0 && pv.rank > 0) wait_flag(L + PW_HFLAG + 0, it, L + PW_ERR, pv.nowait);
-  if (threadIdx.x == 32 && pv.rank < pv.world - 1) wait_flag(L + PW_HFLAG + 1, it, L + PW_ERR, pv.nowait);  // another warp: both polls in flight
+  if (threadIdx.x == 0 && pv.rank > 0) wait_flag(L + PW_HFLAG + 0, it, L + PW_ERR, pv.nowait, pv.timeout_ns);
+  if (threadIdx.x == 32 && pv.rank < pv.world - 1) wait_flag(L + PW_HFLAG + 1, it, L + PW_ERR, pv.nowait, pv.timeout_ns);  // another warp: both polls in flight
   __syncthreads();
-  double dot = spmv_rows<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, p, q, mask, true);
+  double dot = spmv_tiles<GROUP, true>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, p, q, mask, true, sm);
   dot = block_sum(dot, red);
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<double*>(L + PW_ACC) + 0, dot);
   if (arrive_last(L + PW_TICKET, gridDim.x, &sh_last)) {
@@ -163,8 +168,8 @@ __global__ void __launch_bounds__(256) ppcg_update_xr_kernel(int64_t n2, const d
   const uint64_t it = L[PW_IT];
   {  // one warp per quantity, one lane per rank: all lines are polled concurrently
     const int w = threadIdx.x >> 5, k = threadIdx.x & 31;
-    if (w == 0 && k < pv.world) sh_pq[k] = line_wait(L + PW_LL_PQ + 2 * k, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
-    if (w == 1 && k < pv.world) sh_rz[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait);
+    if (w == 0 && k < pv.world) sh_pq[k] = line_wait(L + PW_LL_PQ + 2 * k, (uint32_t)(it + 1), L + PW_ERR, pv.nowait, pv.timeout_ns);
+    if (w == 1 && k < pv.world) sh_rz[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait, pv.timeout_ns);
   }
   __syncthreads();
   double pq = 0.0, rz_old = 0.0;
@@ -223,9 +228,9 @@ __global__ void __launch_bounds__(256) ppcg_update_p_kernel(int64_t own_lo, int6
   {
     const int w = threadIdx.x >> 5, k = threadIdx.x & 31;
     const uint64_t* nw = L + PW_LL_RZ + (it & 1) * 4 * FEM_PEER_MAX + 4 * k;
-    if (w == 0 && k < pv.world) sh_new[k] = line_wait(nw, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
-    if (w == 1 && k < pv.world) sh_rr[k] = line_wait(nw + 2, (uint32_t)(it + 1), L + PW_ERR, pv.nowait);
-    if (w == 2 && k < pv.world) sh_old[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait);
+    if (w == 0 && k < pv.world) sh_new[k] = line_wait(nw, (uint32_t)(it + 1), L + PW_ERR, pv.nowait, pv.timeout_ns);
+    if (w == 1 && k < pv.world) sh_rr[k] = line_wait(nw + 2, (uint32_t)(it + 1), L + PW_ERR, pv.nowait, pv.timeout_ns);
+    if (w == 2 && k < pv.world) sh_old[k] = line_wait(L + PW_LL_RZ + ((it + 1) & 1) * 4 * FEM_PEER_MAX + 4 * k, (uint32_t)it, L + PW_ERR, pv.nowait, pv.timeout_ns);
   }
   __syncthreads();
   double rz_new = 0.0, rz_old = 0.0, rr = 0.0;
@@ -312,6 +317,7 @@ static int make_view(PeerView* pv, void* comm, const void* const* peers, int ran
   pv->rank = rank;
   pv->world = world;
   pv->nowait = g_fem_tuning.peer_nowait;
+  pv->timeout_ns = (uint64_t)(g_fem_tuning.peer_timeout_ms > 0 ? g_fem_tuning.peer_timeout_ms : 10000) * 1000000ull;
   return FEM_OK;
 }
 
@@ -342,12 +348,13 @@ extern "C" int fem_ppcg_spmv_dot(const fem_plan* P, const double* K_vals, const 
   if (rc != FEM_OK) return rc;
   const SpmvShape sh = spmv_shape(P);
   cudaStream_t st = (cudaStream_t)stream;
-#define PSPMV(G, UU) ppcg_spmv_kernel<G, UU><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, p, q, free_mask, pv)
-#define PSPMV_U(G) do { if (sh.unroll == 1) PSPMV(G, 1); else if (sh.unroll == 2) PSPMV(G, 2); else PSPMV(G, 4); } while (0)
-  if (sh.group == 4) PSPMV_U(4);
-  else if (sh.group == 8) PSPMV_U(8);
-  else PSPMV_U(16);
-#undef PSPMV_U
+  FEM_REQUIRE(P->tile_seg != nullptr, "plan without SpMV tiles");
+  const unsigned tb = spmv_tile_blocks(P);
+  const int32_t* tseg = P->tile_seg;
+#define PSPMV(G) ppcg_spmv_kernel<G><<<tb, 256, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, tseg, K_vals, p, q, free_mask, pv)
+  if (sh.group == 4) PSPMV(4);
+  else if (sh.group == 8) PSPMV(8);
+  else PSPMV(16);
 #undef PSPMV
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;

@@ -28,6 +28,8 @@ extern "C" int fem_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "spmv_blocks_per_sm")) g_fem_tuning.spmv_blocks_per_sm = value;
   else if (!strcmp(key, "assemble_variant")) g_fem_tuning.assemble_variant = value;
   else if (!strcmp(key, "spmv_unroll")) g_fem_tuning.spmv_unroll = value;
+  else if (!strcmp(key, "spmv_staged")) g_fem_tuning.spmv_staged = value;
+  else if (!strcmp(key, "peer_timeout_ms")) g_fem_tuning.peer_timeout_ms = value;
   else if (!strcmp(key, "peer_nowait")) g_fem_tuning.peer_nowait = value;
   else {
     fem_set_error("unknown tuning key %s", key);
@@ -443,6 +445,88 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int bo
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// x-staging plan of the SpMV.  One CTA per tile of FEM_SPMV_TILE consecutive nodes: the columns (neighbour nodes) its
+// rows reference are marked in a shared-memory bitmap over [cmin, cmin + WIN); one thread merges the set bits into
+// contiguous ranges (gaps < GAP nodes are bridged); when they fit FEM_SPMV_MAXSEG ranges / FEM_SPMV_CAP nodes, every
+// block gets the position of its column inside the concatenated ranges (nbr_loc), else the tile gathers from global memory.
+// On a structured P1 mesh a tile sees three ranges of 130 nodes (the node rows below, at and above it).
+// ------------------------------------------------------------------------------------------------
+constexpr int SPMV_WIN = 1 << 16;  // nodes covered by the bitmap
+constexpr int SPMV_GAP = 32;
+__global__ void __launch_bounds__(FEM_SPMV_TILE) build_spmv_tiles(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
+                                                                 const int32_t* __restrict__ nbr_idx, int32_t* __restrict__ tile_seg,
+                                                                 uint16_t* __restrict__ nbr_loc, int* n_fallback) {
+  __shared__ uint32_t bits[SPMV_WIN / 32];
+  __shared__ int s_min, s_max, s_nseg, s_start[FEM_SPMV_MAXSEG], s_len[FEM_SPMV_MAXSEG], s_off[FEM_SPMV_MAXSEG];
+  const int64_t tile = blockIdx.x;
+  const int64_t a = tile * FEM_SPMV_TILE + threadIdx.x;
+  int p0 = 0, deg = 0;
+  if (a < n_n) { p0 = nbr_ptr[a]; deg = nbr_ptr[a + 1] - p0; }
+  if (threadIdx.x == 0) { s_min = INT32_MAX; s_max = -1; s_nseg = 0; }
+  for (int w = threadIdx.x; w < SPMV_WIN / 32; w += blockDim.x) bits[w] = 0u;
+  __syncthreads();
+  int cmin = INT32_MAX, cmax = -1;
+  for (int j = 0; j < deg; ++j) { const int c = nbr_idx[p0 + j]; cmin = min(cmin, c); cmax = max(cmax, c); }
+  if (deg > 0) { atomicMin(&s_min, cmin); atomicMax(&s_max, cmax); }
+  __syncthreads();
+  const int lo = s_min, hi = s_max;
+  const bool window_ok = hi >= lo && (hi - lo) < SPMV_WIN;
+  if (window_ok) {
+    for (int j = 0; j < deg; ++j) { const int c = nbr_idx[p0 + j] - lo; atomicOr(&bits[c >> 5], 1u << (c & 31)); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nseg = 0, total = 0;
+    if (window_ok) {
+      int run_start = -1, last = -1;
+      const int nwords = ((hi - lo) >> 5) + 1;
+      for (int w = 0; w < nwords && nseg <= FEM_SPMV_MAXSEG; ++w) {
+        uint32_t m = bits[w];
+        while (m) {
+          const int b = (w << 5) + __ffs(m) - 1;
+          m &= m - 1;
+          if (run_start < 0) { run_start = b; }
+          else if (b - last > SPMV_GAP) {  // close the run
+            if (nseg < FEM_SPMV_MAXSEG) { s_start[nseg] = lo + run_start; s_len[nseg] = last - run_start + 1; s_off[nseg] = total; }
+            total += last - run_start + 1;
+            ++nseg;
+            run_start = b;
+          }
+          last = b;
+        }
+      }
+      if (run_start >= 0) {
+        if (nseg < FEM_SPMV_MAXSEG) { s_start[nseg] = lo + run_start; s_len[nseg] = last - run_start + 1; s_off[nseg] = total; }
+        total += last - run_start + 1;
+        ++nseg;
+      }
+    }
+    const bool ok = window_ok && nseg >= 1 && nseg <= FEM_SPMV_MAXSEG && total <= FEM_SPMV_CAP;
+    int32_t* d = tile_seg + tile * FEM_SPMV_DESC;
+    d[0] = ok ? nseg : 0;
+    d[1] = ok ? total : 0;
+    for (int k = 0; k < FEM_SPMV_MAXSEG; ++k) {
+      d[2 + 2 * k] = (ok && k < nseg) ? s_start[k] : 0;
+      d[3 + 2 * k] = (ok && k < nseg) ? s_len[k] : 0;
+    }
+    s_nseg = ok ? nseg : 0;
+    if (!ok && hi >= lo) atomicAdd(n_fallback, 1);
+  }
+  __syncthreads();
+  const int nseg = s_nseg;
+  for (int j = 0; j < deg; ++j) {
+    uint16_t loc = 0;
+    if (nseg > 0) {
+      const int c = nbr_idx[p0 + j];
+      for (int k = 0; k < nseg; ++k)
+        if (c >= s_start[k] && c < s_start[k] + s_len[k]) loc = (uint16_t)(s_off[k] + (c - s_start[k]));
+    }
+    nbr_loc[p0 + j] = loc;
+  }
+}
+
 typedef CUresult (*fem_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -565,6 +649,20 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     if ((rc = dmalloc(P, &P->row_ptr, P->n_dof + 1)) != FEM_OK) break;
     if ((rc = dmalloc(P, &P->col_idx, P->nnz)) != FEM_OK) break;
     expand_csr<<<grid(n_n), threads, 0, st>>>(n_n, P->nbr_ptr, P->nbr_idx, P->row_ptr, P->col_idx);
+    // x-staging plan of the SpMV
+    P->n_tiles = (n_n + FEM_SPMV_TILE - 1) / FEM_SPMV_TILE;
+    if ((rc = dmalloc(P, &P->tile_seg, P->n_tiles * FEM_SPMV_DESC)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->nbr_loc, n_blocks)) != FEM_OK) break;
+    {
+      int* nfb = nullptr;
+      if (cudaMalloc(&nfb, sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc nfb"); break; }
+      cudaMemsetAsync(nfb, 0, sizeof(int), st);
+      build_spmv_tiles<<<(unsigned)P->n_tiles, FEM_SPMV_TILE, 0, st>>>(n_n, P->nbr_ptr, P->nbr_idx, P->tile_seg, P->nbr_loc, nfb);
+      int h_nfb = 0;
+      cudaMemcpy(&h_nfb, nfb, sizeof(int), cudaMemcpyDeviceToHost);
+      cudaFree(nfb);
+      P->spmv_fallback_tiles = h_nfb;
+    }
     // SELL-32 incidence storage
     P->n_slices = (n_n + 31) / 32;
     if (cudaMalloc(&width32, sizeof(int32_t) * (P->n_slices + 1)) != cudaSuccess ||
@@ -681,7 +779,7 @@ extern "C" int fem_plan_create(int64_t n_n, int64_t n_e, int n_p, int n_q, const
 
 extern "C" int fem_plan_destroy(fem_plan* P) {
   if (!P) return FEM_OK;
-  cudaFree(P->stage_box); cudaFree(P->inc_stage);
+  cudaFree(P->stage_box); cudaFree(P->inc_stage); cudaFree(P->tile_seg); cudaFree(P->nbr_loc);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
   cudaFree(P->geom); cudaFree(P->dscratch);

@@ -28,12 +28,42 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
   }
 }
 
+// x staged through shared memory by bulk async copies (spmv.cuh: spmv_tiles)
+template <int GROUP>
+__global__ void __launch_bounds__(256) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+                                                         const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
+                                                         const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
+                                                         const double* __restrict__ x, double* __restrict__ y,
+                                                         const uint8_t* __restrict__ mask, double* dot_out, double* zero_a, double* zero_b) {
+  __shared__ double red[32];
+  __shared__ SpmvTileSmem sm;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (zero_a) *zero_a = 0.0;
+    if (zero_b) *zero_b = 0.0;
+  }
+  double dot = spmv_tiles<GROUP, false>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, y, mask, dot_out != nullptr, sm);
+  if (dot_out) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+  }
+}
+
 static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x, double* y, const uint8_t* mask,
                        double* dot, double* zero_a, double* zero_b, cudaStream_t st) {
   FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
   const SpmvShape sh = spmv_shape(P);
   const int threads = 256, group = sh.group, unroll = sh.unroll;
+  if (spmv_use_tiles(P)) {
+    const unsigned tb = spmv_tile_blocks(P);
+#define SPMVT(G) spmv_tiles_kernel<G><<<tb, threads, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b)
+    if (group == 4) SPMVT(4);
+    else if (group == 8) SPMVT(8);
+    else SPMVT(16);
+#undef SPMVT
+    FEM_CUDA_CHECK(cudaGetLastError());
+    return FEM_OK;
+  }
   const unsigned blocks = sh.blocks;
 #define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b)
 #define SPMV_U(G) do { if (unroll == 1) SPMV(G, 1); else if (unroll == 2) SPMV(G, 2); else SPMV(G, 4); } while (0)

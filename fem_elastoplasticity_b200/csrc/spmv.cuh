@@ -84,6 +84,172 @@ __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __
   return dot;
 }
 
+
+// ---- x staged in shared memory ------------------------------------------------------------------------------------
+// A CTA walks tiles of FEM_SPMV_TILE consecutive nodes.  The columns a tile references are <= FEM_SPMV_MAXSEG contiguous
+// node ranges of x (plan: tile_seg); one thread brings them into shared memory with bulk async copies (cp.async.bulk ->
+// UBLKCP, completion on an mbarrier) while all threads already stream the tile's matrix values; the gather then reads
+// shared memory through the 16-bit positions of nbr_loc.  x is read once per tile (three tiles share a node row and meet
+// in L2) instead of once per block through L1/L2, and the index stream is 2 B instead of 4 B per block.  The copies of
+// tile i+1 are issued before tile i is computed (two buffers).  Tiles whose columns do not fit gather from global memory.
+__device__ __forceinline__ uint32_t spmv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct SpmvTileSmem {
+  double2 xbuf[2][FEM_SPMV_CAP];
+  uint64_t bar[2];
+};
+
+// thread 0: expect the bytes of the tile's ranges and issue the copies
+__device__ __forceinline__ void spmv_issue_tile(const int32_t* __restrict__ tile_seg, int64_t tile, const double* x, double2* dst, uint64_t* bar) {
+  const int32_t* d = tile_seg + tile * FEM_SPMV_DESC;
+  const int nseg = d[0];
+  if (nseg <= 0) return;
+  const uint32_t b = spmv_smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)d[1] * 16u) : "memory");
+  int off = 0;
+  for (int k = 0; k < nseg; ++k) {
+    const int start = d[2 + 2 * k], len = d[3 + 2 * k];
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(spmv_smem_u32(dst + off)),
+                 "l"(reinterpret_cast<const double2*>(x) + start), "r"((uint32_t)len * 16u), "r"(b)
+                 : "memory");
+    off += len;
+  }
+}
+
+__device__ __forceinline__ void spmv_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t b = spmv_smem_u32(bar);
+  uint32_t ok = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(b), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+template <bool COHERENT>
+__device__ __forceinline__ double2 spmv_ldx(const double* x, int m) {
+  // COHERENT: x may be stored by a peer GPU while the kernel is resident (fused multi-GPU PCG): no non-coherent loads
+  return COHERENT ? __ldcg(reinterpret_cast<const double2*>(x) + m) : __ldg(reinterpret_cast<const double2*>(x) + m);
+}
+
+// blockDim.x == 256.  Returns this thread's share of x'y when want_dot.
+template <int GROUP, bool COHERENT>
+__device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+                                             const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
+                                             const int32_t* __restrict__ tile_seg, const double* __restrict__ vals, const double* x,
+                                             double* __restrict__ y, const uint8_t* __restrict__ mask, const bool want_dot,
+                                             SpmvTileSmem& sm) {
+  constexpr int U = 2, B = 2;                  // row pairs in flight per lane group, blocks per lane loaded up front
+  constexpr int GPC = 256 / GROUP;             // lane groups per CTA
+  constexpr int NPS = GPC * U;                 // nodes per sweep
+  constexpr int SWEEPS = FEM_SPMV_TILE / NPS;
+  static_assert(FEM_SPMV_TILE % NPS == 0, "tile size");
+  const int sub = threadIdx.x % GROUP, gi = threadIdx.x / GROUP;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spmv_smem_u32(&sm.bar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spmv_smem_u32(&sm.bar[1])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (COHERENT) asm volatile("fence.proxy.async;" ::: "memory");  // peer stores observed through the flags precede the async-proxy reads
+    if ((int64_t)blockIdx.x < n_tiles) spmv_issue_tile(tile_seg, blockIdx.x, x, sm.xbuf[0], &sm.bar[0]);
+  }
+  __syncthreads();
+  uint32_t phase[2] = {0u, 0u};
+  double dot = 0.0;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < n_tiles) spmv_issue_tile(tile_seg, next, x, sm.xbuf[cur ^ 1], &sm.bar[cur ^ 1]);
+    const bool staged = tile_seg[tile * FEM_SPMV_DESC] > 0;  // CTA-uniform
+    const double2* xs = sm.xbuf[cur];
+    bool waited = false;
+#pragma unroll 1
+    for (int sw = 0; sw < SWEEPS; ++sw) {
+      int p0[U], deg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
+        p0[u] = 0;
+        deg[u] = 0;
+        if (a < n_n) {
+          p0[u] = __ldg(nbr_ptr + a);
+          deg[u] = __ldg(nbr_ptr + a + 1) - p0[u];
+        }
+      }
+      int m[U][B];
+      double2 v0[U][B], v1[U][B];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const int j = sub + b * GROUP;
+          m[u][b] = 0;
+          v0[u][b] = v1[u][b] = make_double2(0.0, 0.0);
+          if (j < deg[u]) {
+            const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
+            m[u][b] = staged ? (int)__ldcs(nbr_loc + p0[u] + j) : __ldg(nbr_idx + p0[u] + j);
+            v0[u][b] = __ldcs(row0 + j);
+            v1[u][b] = __ldcs(row0 + deg[u] + j);
+          }
+        }
+      if (staged && !waited) {  // the matrix values above are in flight while the x ranges arrive
+        spmv_bar_wait(&sm.bar[cur], phase[cur]);
+        waited = true;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const int j = sub + b * GROUP;
+          if (j < deg[u]) {
+            const double2 xv = staged ? xs[m[u][b]] : spmv_ldx<COHERENT>(x, m[u][b]);
+            acc0 = fma(v0[u][b].x, xv.x, acc0);
+            acc0 = fma(v0[u][b].y, xv.y, acc0);
+            acc1 = fma(v1[u][b].x, xv.x, acc1);
+            acc1 = fma(v1[u][b].y, xv.y, acc1);
+          }
+        }
+        for (int j = sub + B * GROUP; j < deg[u]; j += GROUP) {  // rows longer than B*GROUP blocks
+          const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
+          const double2 w0 = __ldcs(row0 + j), w1 = __ldcs(row0 + deg[u] + j);
+          const double2 xx = staged ? xs[__ldcs(nbr_loc + p0[u] + j)] : spmv_ldx<COHERENT>(x, __ldg(nbr_idx + p0[u] + j));
+          acc0 = fma(w0.x, xx.x, acc0);
+          acc0 = fma(w0.y, xx.y, acc0);
+          acc1 = fma(w1.x, xx.x, acc1);
+          acc1 = fma(w1.y, xx.y, acc1);
+        }
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) {
+          acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+          acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
+        if (sub == 0 && a < n_n) {
+          if (mask) {
+            const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
+            if (!mk.x) acc0 = 0.0;
+            if (!mk.y) acc1 = 0.0;
+          }
+          reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
+          if (want_dot) {
+            const double2 xa = spmv_ldx<COHERENT>(x, (int)a);
+            dot = fma(xa.x, acc0, dot);
+            dot = fma(xa.y, acc1, dot);
+          }
+        }
+      }
+    }
+    if (staged) {
+      if (!waited) spmv_bar_wait(&sm.bar[cur], phase[cur]);
+      phase[cur] ^= 1u;
+    }
+    __syncthreads();  // xbuf[cur] may be refilled (by the copies for tile it+2, issued at the top of the next iteration)
+  }
+  return dot;
+}
+
 // lanes per node by block-row length (P1: 7 blocks per row pair -> 2 per lane), nodes in flight, persistent grid size
 struct SpmvShape { int group, unroll; unsigned blocks; };
 static inline SpmvShape spmv_shape(const fem_plan* P) {
@@ -98,4 +264,11 @@ static inline SpmvShape spmv_shape(const fem_plan* P) {
   if (blocks < 1) blocks = 1;
   s.blocks = (unsigned)blocks;
   return s;
+}
+static inline bool spmv_use_tiles(const fem_plan* P) { return P->tile_seg != nullptr && g_fem_tuning.spmv_staged != 1; }
+static inline unsigned spmv_tile_blocks(const fem_plan* P) {
+  int64_t blocks = P->n_tiles;
+  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 6);
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
 }

@@ -16,6 +16,15 @@ import torch
 import torch.distributed as dist
 
 
+class PCGNotConverged(ArithmeticError):
+    """Raised by the distributed / two-level solves when ``maxit`` iterations did not reach ``rtol`` (the single-GPU
+    fem_pcg returns FEM_ERR_PCG_MAXIT in the same situation).  ``x`` holds the last iterate."""
+
+    def __init__(self, what, iters, relres, rtol):
+        super().__init__(f"{what}: relative residual {relres:.3e} > rtol {rtol:.1e} after {iters} iterations")
+        self.iters, self.relres, self.rtol = iters, relres, rtol
+
+
 class StripPartition:
     """Rank r owns cell rows [r*ny_loc, (r+1)*ny_loc) of an nx x ny_global uniform P1 mesh and the node rows
     (r*ny_loc, (r+1)*ny_loc] (rank 0 also owns node row 0): interface nodes belong to the lower rank."""
@@ -245,6 +254,13 @@ class DistributedPCG:
         o.pcg_init(rhs, None, self.mask, self.minv, self.r, self.p, scal)
         part.all_reduce(scal[0:5])
         n_it = iters if iters is not None else maxit
+        self.relres = float("nan")
+        if iters is None:                                 # already converged (zero right-hand side, exact initial guess)?
+            h = scal.cpu()
+            self.relres = float((h[1] / h[4]).sqrt()) if h[4] > 0 else 0.0
+            if self.relres <= rtol:
+                part.halo_exchange(self.x)
+                return self.x, 0
         if self.fused:
             return self._solve_fused(k_vals, n_it, iters is None, rtol, check_every)
         it = 0
@@ -278,13 +294,16 @@ class DistributedPCG:
                 iteration(it)
                 it += 1
                 self.launches_last += 3
-            if iters is None and it % check_every == 0:
+            if iters is None and (it % check_every == 0 or it == n_it):
                 h = scal.cpu()
                 if not torch.isfinite(h[1]):
                     raise ArithmeticError("PCG breakdown: residual is not finite")
+                self.relres = float((h[1] / h[4]).sqrt()) if h[4] > 0 else 0.0
                 if h[1] <= rtol * rtol * h[4]:
                     break
         part.halo_exchange(self.x)
+        if iters is None and self.relres > rtol:
+            raise PCGNotConverged("distributed PCG", it, self.relres, rtol)
         return self.x, it
 
     GRAPH_CHUNK = 10
@@ -329,18 +348,29 @@ class DistributedPCG:
                         self.graph_error, self.use_graph_fused, g = repr(e), False, None
             it += n
             self.launches_last += 3 * n
-            if check and it % check_every == 0:
+            if check and (it % check_every == 0 or it == n_it):
                 if bb is None:
                     bb = float(self.scal[4].item())
+                self._check_peer_error()                 # all ranks decide together: a timed-out rank's r'r is garbage
                 rr = float(out[1].item())
                 if rr != rr or rr == float("inf"):
                     raise ArithmeticError("PCG breakdown: residual is not finite")
+                self.relres = (rr / bb) ** 0.5 if bb > 0 else 0.0
                 if rr <= rtol * rtol * bb:
                     break
-        if int(peer.comm[self.WORD_ERR].item()) != 0:
-            raise RuntimeError("fused PCG: a peer did not publish within 2 s (rank %d)" % part.rank)
+        self._check_peer_error()
         part.halo_exchange(self.x)
+        if check and self.relres > rtol:
+            raise PCGNotConverged("fused distributed PCG", it, self.relres, rtol)
         return self.x, it
+
+    def _check_peer_error(self):
+        """The sticky time-out word of the fused kernels, MAX-reduced over the ranks so that every rank raises together
+        (a rank that carried on alone would hang in the next collective)."""
+        err = self.peer.comm[self.WORD_ERR:self.WORD_ERR + 1].clone()
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if int(err.item()) != 0:
+            raise RuntimeError("fused PCG: a peer did not publish within the time-out (tuning key peer_timeout_ms); detected on rank %d" % self.part.rank)
 
     def _pair_graph(self, k_vals, iteration):
         """CUDA graph of iterations (0, 1) - the kernels only depend on the parity of the iteration index.  Captured after

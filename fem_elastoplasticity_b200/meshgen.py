@@ -52,6 +52,45 @@ def synthetic_strain(n_int, device="cuda", seed=0, mean=(-3e-4, -3e-4, 0.0), std
     return e
 
 
+def _s64(v):
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def hash_uniform(counter):
+    """Counter-based uniform numbers in (0, 1): splitmix64 of an int64 tensor of counters (wrap-around int64 arithmetic,
+    logical shifts emulated by masking).  A value depends only on its counter, so ranks of a partitioned mesh that share
+    an element or a node generate identical data for it, whatever their local numbering."""
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+    z = counter + _s64(0x9E3779B97F4A7C15)
+    z = (z ^ lsr(z, 30)) * _s64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * _s64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    return (lsr(z, 11).to(torch.float64) + 0.5) * (1.0 / float(1 << 53))
+
+
+def hash_normal(ids, stream, seed=0):
+    """Standard normal numbers (Box-Muller on two hashed uniforms) indexed by global ids: value = f(seed, stream, id)."""
+    base = (ids.to(torch.int64) * 16 + 2 * int(stream)) + int(seed) * 1000003 * 16
+    u1, u2 = hash_uniform(base), hash_uniform(base + 1)
+    return torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * np.pi * u2)
+
+
+def synthetic_strain_global(n_int, first_id=0, device="cuda", seed=0, mean=(-3e-4, -3e-4, 0.0), std=2e-4):
+    """Like ``synthetic_strain`` (same distribution: ~2 % plastic / 0.6 % apex at the footing constants) but a function of
+    the GLOBAL integration-point id ``first_id + local index``: the ghost cell row a rank keeps for its interface nodes
+    carries exactly the strains its owner has, so the partitioned matrix is the matrix of one global problem."""
+    ids = torch.arange(first_id, first_id + n_int, dtype=torch.int64, device=device)
+    return torch.stack([hash_normal(ids, k, seed) * std + mean[k] for k in range(3)])
+
+
+def synthetic_nodal_global(n_n, first_node=0, device="cuda", seed=1, scale=1e-3):
+    """DOF vector (2 n_n,) of hashed normals indexed by global node id (consistent on ghost node rows)."""
+    ids = torch.arange(first_node, first_node + n_n, dtype=torch.int64, device=device)
+    return (torch.stack([hash_normal(ids, 8 + k, seed) for k in range(2)], dim=1).reshape(-1) * scale).contiguous()
+
+
 def create_midpoints_p2(coord, elem):
     """P1 -> P2 enrichment with the numbering of the reference's create_midpoints_P2 (tsx-tunnel/pythonFEM.py:1508-1626),
     without its O(n_e^2) ``np.where`` walk: every edge is keyed by its vertex pair, a midpoint is numbered by the FIRST

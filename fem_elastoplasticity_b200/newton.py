@@ -21,7 +21,7 @@ from .plan import FemPlan, axpby, dp_return_map
 
 class NewtonSolver:
     def __init__(self, plan: FemPlan, shear, bulk, eta, c, q_mask, pcg_rtol=1e-13, pcg_maxit=200000, check_every=50,
-                 tangent_mode="direct", precond="jacobi", coarse_cells=64, part=None, halo="auto"):
+                 tangent_mode="direct", precond="jacobi", coarse_cells=64, part=None, halo="auto", refine=0):
         self.plan = plan
         dev = plan.device
         f = plan._f64
@@ -36,6 +36,7 @@ class NewtonSolver:
             self.mask = self.free & part.owned_mask(dev)
             self._dpcg = DistributedPCG(plan, part, self.mask, peer=halo)
         self.pcg_rtol, self.pcg_maxit, self.check_every = pcg_rtol, pcg_maxit, check_every
+        self.refine = refine                               # iterative-refinement steps of the single-GPU Jacobi solve (FemPlan.pcg)
         self.tangent_mode = tangent_mode
         self.precond, self.coarse_cells, self._tl = precond, coarse_cells, None   # "jacobi" | "twolevel" (see twolevel.py)
         self.k_elast = plan.assemble_elastic(self.shear, self.bulk)
@@ -64,9 +65,9 @@ class NewtonSolver:
             return x.clone(), its, rel
         if self._dpcg is not None:                        # ghost rows of the returned vector are current
             x, its = self._dpcg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every)
-            return x.clone(), its, None
+            return x.clone(), its, self._dpcg.relres     # solve() raises PCGNotConverged when maxit is reached
         return self.plan.pcg(k_vals, rhs, self.mask, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every,
-                             x0=x0, work=self.work)
+                             x0=x0, work=self.work, refine=self.refine)
 
     def criterion(self, du, u_it, u_new):
         """q1/(q2+q3) with q = sqrt(v' K_elast v)   (Plasticity2D_DP/pythonFEM.py:1072-1075)"""
@@ -105,7 +106,7 @@ class NewtonSolver:
 
 
 def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi",
-                   coarse_cells=64, part=None, halo="auto"):
+                   coarse_cells=64, part=None, halo="auto", refine=0):
     """Strip-footing load stepping of Plasticity2D_DP.elasticity_fem (:986-1131) on the device.
     ``mesh``: dict with coordinates (2,n_n), elements (3,n_e), Q, dirichlet_nodes (NumPy or CUDA tensors).
     ``part``: a distributed.StripPartition when run one process per GPU; ``mesh`` is then this rank's ``part.local_mesh``
@@ -120,7 +121,7 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
     G, Kb, eta, c = footing_materials(P.n_int, dev)
     c0 = 450
     ns = NewtonSolver(P, G, Kb, eta, c, mesh["Q"], pcg_rtol=pcg_rtol, tangent_mode=tangent_mode, precond=precond, coarse_cells=coarse_cells,
-                      part=part, halo=halo)
+                      part=part, halo=halo, refine=refine)
     dn = torch.as_tensor(np.asarray(mesh["dirichlet_nodes"].cpu() if isinstance(mesh["dirichlet_nodes"], torch.Tensor)
                                     else mesh["dirichlet_nodes"], dtype=np.float64)).to(dev)
     q_nd = dn[1] > 0
@@ -180,7 +181,7 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
             "Ep": ep_old.cpu().numpy()}
 
 
-def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi", coarse_cells=8):
+def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi", coarse_cells=8, refine=0):
     """tsx-tunnel load stepping (tsx-tunnel/pythonFEM.py:1661-1830) for P1 on the device."""
     from . import pythonFEM as api
     et = api.LagrangeElementType.P1
@@ -205,7 +206,7 @@ def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct
     n_int = P.n_int
     ones = np.ones(n_int)
     ns = NewtonSolver(P, shear0 * ones, bulk0 * ones, eta0 * ones, c0 * ones, q, pcg_rtol=pcg_rtol, tangent_mode=tangent_mode,
-                      precond=precond, coarse_cells=coarse_cells)
+                      precond=precond, coarse_cells=coarse_cells, refine=refine)
     s_init = torch.as_tensor(np.tile(s0.reshape(-1, 1), (1, n_int))).to(P.device)
     f0 = P.internal_force(s_init)                                     # :1737
     rhs = axpby(-1.0, f0, 0.0, f0)

@@ -150,4 +150,7 @@ class TwoLevelPCG:
                     break
         if part is not None:
             part.halo_exchange(self.x)
+        if iters is None and not rel <= rtol:
+            from .distributed import PCGNotConverged
+            raise PCGNotConverged("two-level PCG", it, rel, rtol)
         return self.x, it, rel

@@ -155,7 +155,8 @@ int fem_pcg_update_p_push(int64_t own_lo, int64_t own_hi, const double* r, const
  * One iteration = fem_ppcg_spmv_dot, fem_ppcg_update_xr, fem_ppcg_update_p, the same number on every rank.
  * fem_ppcg_update_p: [own_lo, own_hi) = owned DOF range; p[src_up : src_up+n_up] is also stored to dst_up (the upper
  *   neighbour's ghost row, NULL if none), likewise *_lo.  Words FEM_PPCG_WORD_OUT, +1 of comm then hold the global r'z and
- *   r'r (doubles) and word FEM_PPCG_WORD_ERR is non-zero if a wait timed out (2 s; the results are then invalid).                         */
+ *   r'r (doubles) and word FEM_PPCG_WORD_ERR is non-zero if a wait timed out (10 s, tuning key "peer_timeout_ms"; the results are
+ *   then invalid).                         */
 #define FEM_PPCG_WORDS 176     /* 8-byte words of a communication block */
 #define FEM_PPCG_WORD_ERR 167  /* non-zero: a wait timed out */
 #define FEM_PPCG_WORD_OUT 172  /* two doubles: global r'z, r'r after the last finished iteration */
@@ -210,7 +211,8 @@ int fem_vec_axpby(int64_t n, double a, const double* x, double b, const double* 
  * points of the elements around node n (Plasticity2D_DP/pythonFEM.py:760-816)                      */
 int fem_transform(const fem_plan* plan, const double* q_int, double* q_node, fem_stream stream);
 
-/* launch-shape knobs for benchmarking ("return_map_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm");
+/* launch-shape knobs for benchmarking ("return_map_variant", "assemble_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm",
+ * "spmv_staged", "peer_timeout_ms");
  * value 0 restores the default.  Results never depend on them.                                     */
 int fem_set_tuning(const char* key, int value);
 

@@ -276,7 +276,7 @@ def test_large_mesh_properties(fem):
     S4 = torch.randn((4, P.n_int), dtype=torch.float64, device="cuda", generator=g)
     ref = None
     try:
-        for v in (6, 7, 2, 1):
+        for v in (8, 6, 7, 2, 1):
             _lib.call("fem_set_tuning", b"assemble_variant", v)
             got = (P.assemble_elastic(G, Kb), *P.assemble_tangent_force(r["ds"], S4), P.assemble_tangent_ref(r["ds"], G, Kb, kel))
             if ref is None:
@@ -304,7 +304,7 @@ def test_assembly_variants_agree_bitwise(fem, golden):
     P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
     res = {}
     try:
-        for v in (1, 2, 6, 7):
+        for v in (1, 2, 6, 7, 8):
             _lib.call("fem_set_tuning", b"assemble_variant", v)
             kel = P.assemble_elastic(G, Kb)
             kt, F = P.assemble_tangent_force(g["ds"], g["s"])
@@ -312,7 +312,7 @@ def test_assembly_variants_agree_bitwise(fem, golden):
             res[v] = [t.cpu().numpy() for t in (kel, kt, F, ktr)]
     finally:
         _lib.call("fem_set_tuning", b"assemble_variant", 0)
-    for v in (2, 6, 7):
+    for v in (2, 6, 7, 8):
         for a, b in zip(res[1], res[v]):
             assert np.array_equal(a, b), v
     assert_csr_bits(P.to_scipy_csr(fem["torch"].as_tensor(res[2][3]).cuda()), csr_from(g, "Kt"))
