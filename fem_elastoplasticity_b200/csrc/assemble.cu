@@ -520,7 +520,7 @@ __device__ __forceinline__ void issue_box(const StageMaps& M, unsigned char* bb,
 }
 
 template <int MODE, bool FORCE, int MAXDEG, int BW>
-__global__ void __launch_bounds__(192) assemble_rows_tmap_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
+__global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
   constexpr int NP = 3;
   using L = StageLayout<MODE, FORCE>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -925,19 +925,19 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A, M);
   } else {                                   // persistent, software-pipelined: D (register accumulators) or E (shared-memory accumulators)
-    const bool ps = g_fem_tuning.assemble_variant != 6;  // E unless D is asked for
+    const bool ps = g_fem_tuning.assemble_variant == 8;  // D unless E is asked for (E is shared-memory-bandwidth bound: profiles/r2c)
     void (*kern)(const AsmArgs, const StageMaps) =
         ps ? ((bw == 66) ? assemble_rows_ps_kernel<MODE, FORCE, 8, 66> : assemble_rows_ps_kernel<MODE, FORCE, 8, 0>)
            : ((bw == 66) ? assemble_rows_tmap_kernel<MODE, FORCE, 8, 66> : assemble_rows_tmap_kernel<MODE, FORCE, 8, 0>);
     const size_t per_warp = (size_t)L::warp_b(bw) + (ps ? 8 * 2 * 32 * 16 : 0);
     // warps per CTA that packs the most warps into the 227 KB of an SM (1 KB per CTA is reserved)
     int best = 0;
-    for (int w = (ps ? 1 : 4); w <= (ps ? 8 : 6); ++w) {
+    for (int w = (ps ? 1 : 4); w <= (ps ? 8 : 11); ++w) {
       const size_t sm = (size_t)w * per_warp;
       const int per = (int)((227 * 1024) / (sm + 1024));
       if (per * w >= best) { best = per * w; warps = w; }
     }
-    if (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= (ps ? 8 : 6)) warps = g_fem_tuning.assemble_warps;
+    if (g_fem_tuning.assemble_warps >= 1 && g_fem_tuning.assemble_warps <= (ps ? 8 : 11)) warps = g_fem_tuning.assemble_warps;
     smem = (size_t)warps * per_warp;
     if (smem > 227 * 1024) return -1;
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -15,9 +15,10 @@
 #define FEM_WARP 32
 #define FEM_INVALID_KEY 0xFFFFFFFFu
 #define FEM_SLICE_COUNTERS 64  // dynamic-scheduler counters per plan (dscratch[8 .. 8 + FEM_SLICE_COUNTERS))
-#define FEM_SPMV_TILE 128      // nodes (row pairs) per SpMV tile
+#define FEM_SPMV_TILE 256      // nodes (row pairs) per SpMV tile
+#define FEM_SPMV_THREADS (2 * FEM_SPMV_TILE)  // CTA size of the tiled SpMV kernels: 4 lanes per node, 2 nodes in flight per lane group
 #define FEM_SPMV_MAXSEG 4      // contiguous column ranges per tile
-#define FEM_SPMV_CAP 512       // staged x entries (nodes) per tile: 8 KB of shared memory per buffer
+#define FEM_SPMV_CAP 1024      // staged x entries (nodes) per tile: 16 KB of shared memory per buffer
 #define FEM_SPMV_DESC 12       // int32 words per tile descriptor
 #define FEM_STAGE_MAXBOXW 96   // widest TMA box (elements); longer runs are split
 // 2-D tensor map over `rows` SoA rows of n_int doubles (row stride n_int), box = rows x boxw

@@ -127,7 +127,7 @@ __device__ __forceinline__ bool arrive_last(uint64_t* ticket_word, const unsigne
 // neighbour GPUs while this kernel is already resident (it spins on the halo flags), so every load of p is a coherent
 // one (bulk async copies after a proxy fence, or ld.global.cg in the gather fallback).
 template <int GROUP>
-__global__ void __launch_bounds__(256) ppcg_spmv_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS) ppcg_spmv_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                         const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                         const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                         const double* p, double* __restrict__ q,
@@ -351,7 +351,7 @@ extern "C" int fem_ppcg_spmv_dot(const fem_plan* P, const double* K_vals, const 
   FEM_REQUIRE(P->tile_seg != nullptr, "plan without SpMV tiles");
   const unsigned tb = spmv_tile_blocks(P);
   const int32_t* tseg = P->tile_seg;
-#define PSPMV(G) ppcg_spmv_kernel<G><<<tb, 256, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, tseg, K_vals, p, q, free_mask, pv)
+#define PSPMV(G) ppcg_spmv_kernel<G><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, tseg, K_vals, p, q, free_mask, pv)
   if (sh.group == 4) PSPMV(4);
   else if (sh.group == 8) PSPMV(8);
   else PSPMV(16);

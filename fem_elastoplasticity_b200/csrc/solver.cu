@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
 
 // x staged through shared memory by bulk async copies (spmv.cuh: spmv_tiles)
 template <int GROUP>
-__global__ void __launch_bounds__(256) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                          const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                          const double* __restrict__ x, double* __restrict__ y,
@@ -56,7 +56,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
   const int threads = 256, group = sh.group, unroll = sh.unroll;
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
-#define SPMVT(G) spmv_tiles_kernel<G><<<tb, threads, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b)
+#define SPMVT(G) spmv_tiles_kernel<G><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b)
     if (group == 4) SPMVT(4);
     else if (group == 8) SPMVT(8);
     else SPMVT(16);

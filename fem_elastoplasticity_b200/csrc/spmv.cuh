@@ -5,6 +5,14 @@
 
 // y = mask .* (K x) over all nodes assigned to this thread's warp (grid-stride); returns this thread's share of x'y
 // when want_dot (only lanes with sub == 0 contribute).
+// x gather with an L2 evict_last policy: the matrix values stream through L2 (ld.global.cs) and would otherwise push the
+// few node rows of x the active window needs out of it
+__device__ __forceinline__ double2 ldg_x_keep(const double* x, int m, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(x) + m), "l"(pol));
+  return v;
+}
+
 template <int GROUP, int U>
 __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __restrict__ nbr_ptr,
                                             const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
@@ -16,6 +24,8 @@ __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   constexpr int NPW = GPW * U;  // nodes per warp per sweep: U independent row pairs in flight per lane group
   double dot = 0.0;
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   for (int64_t nb = warp_global * NPW; nb < n_n; nb += n_warps * NPW) {
     int p0[U], deg[U];
 #pragma unroll
@@ -44,7 +54,7 @@ __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       xv[u] = make_double2(0.0, 0.0);
-      if (sub < deg[u]) xv[u] = __ldg(reinterpret_cast<const double2*>(x) + m[u]);
+      if (sub < deg[u]) xv[u] = ldg_x_keep(x, m[u], pol);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -54,7 +64,7 @@ __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __
         const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
         const int mm = __ldg(nbr_idx + p0[u] + j);
         const double2 w0 = __ldcs(row0 + j), w1 = __ldcs(row0 + deg[u] + j);
-        const double2 xx = __ldg(reinterpret_cast<const double2*>(x) + mm);
+        const double2 xx = ldg_x_keep(x, mm, pol);
         acc0 = fma(w0.x, xx.x, acc0);
         acc0 = fma(w0.y, xx.y, acc0);
         acc1 = fma(w1.x, xx.x, acc1);
@@ -133,7 +143,7 @@ __device__ __forceinline__ double2 spmv_ldx(const double* x, int m) {
   return COHERENT ? __ldcg(reinterpret_cast<const double2*>(x) + m) : __ldg(reinterpret_cast<const double2*>(x) + m);
 }
 
-// blockDim.x == 256.  Returns this thread's share of x'y when want_dot.
+// blockDim.x == FEM_SPMV_THREADS.  Returns this thread's share of x'y when want_dot.
 template <int GROUP, bool COHERENT>
 __device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                              const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
@@ -141,7 +151,7 @@ __device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_
                                              double* __restrict__ y, const uint8_t* __restrict__ mask, const bool want_dot,
                                              SpmvTileSmem& sm) {
   constexpr int U = 2, B = 2;                  // row pairs in flight per lane group, blocks per lane loaded up front
-  constexpr int GPC = 256 / GROUP;             // lane groups per CTA
+  constexpr int GPC = FEM_SPMV_THREADS / GROUP;  // lane groups per CTA
   constexpr int NPS = GPC * U;                 // nodes per sweep
   constexpr int SWEEPS = FEM_SPMV_TILE / NPS;
   static_assert(FEM_SPMV_TILE % NPS == 0, "tile size");
@@ -268,7 +278,7 @@ static inline SpmvShape spmv_shape(const fem_plan* P) {
 static inline bool spmv_use_tiles(const fem_plan* P) { return P->tile_seg != nullptr && g_fem_tuning.spmv_staged != 1; }
 static inline unsigned spmv_tile_blocks(const fem_plan* P) {
   int64_t blocks = P->n_tiles;
-  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 6);
+  const int64_t cap = (int64_t)P->sm_count * (g_fem_tuning.spmv_blocks_per_sm > 0 ? g_fem_tuning.spmv_blocks_per_sm : 65536 / (64 * FEM_SPMV_THREADS));  // one resident wave (64 registers)
   if (blocks > cap) blocks = cap;
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }

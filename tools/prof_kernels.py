@@ -35,10 +35,11 @@ for _ in range(a.reps):
         dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm)
     else:
         dp_return_map(Es, ep, G, Kb, eta, c, want_ep=False, out=rm) if not rm else None
-    if a.only in ("all", "assemble"):
+    if a.only in ("all", "assemble", "elastic"):
         P.assemble_elastic(G, Kb, out=k)
+    if a.only in ("all", "assemble", "tangent_force", "tf_spmv"):
         P.assemble_tangent_force(rm["ds"], rm["s"], out_k=k, out_f=F)
-    if a.only in ("all", "spmv"):
+    if a.only in ("all", "spmv", "tf_spmv"):
         P.spmv(k, u, mask=mask, out=y, dot=dot)
     if a.only in ("all", "strain"):
         P.strain(u)

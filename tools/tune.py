@@ -78,16 +78,20 @@ def main():
     mask = P.mask_u8(m["Q"])
     dot = torch.zeros(1, dtype=torch.float64, device="cuda")
     y_ref = None
-    for g in (4, 8):
-        for un in (2, 4):
-            for bps in (8, 16, 32):
-                knob("spmv_group", g), knob("spmv_unroll", un), knob("spmv_blocks_per_sm", bps)
-                res[f"spmv_g{g}_u{un}_b{bps}_ms"] = timeit(lambda: P.spmv(kel_ref, u, mask=mask, out=y, dot=dot))
-                if y_ref is None:
-                    y_ref = y.clone()
-                else:
-                    res[f"spmv_g{g}_u{un}_b{bps}_maxdiff"] = float((y - y_ref).abs().max() / y_ref.abs().max())
-    knob("spmv_group", 0), knob("spmv_unroll", 0), knob("spmv_blocks_per_sm", 0)
+    for staged in (1, 0):                                # 1: round-1 kernel (x gathered through L1/L2); 0: x staged in shared memory
+        knob("spmv_staged", staged)
+        for bps in ((8,) if staged else (1, 2, 3, 4)):
+            knob("spmv_blocks_per_sm", bps)
+            res[f"spmv_{'gather' if staged else 'staged'}_b{bps}_ms"] = timeit(lambda: P.spmv(kel_ref, u, mask=mask, out=y, dot=dot))
+            if y_ref is None:
+                y_ref = y.clone()
+            else:
+                res[f"spmv_{'gather' if staged else 'staged'}_b{bps}_maxdiff"] = float((y - y_ref).abs().max() / y_ref.abs().max())
+    knob("spmv_staged", 0), knob("spmv_blocks_per_sm", 0)
+    for w in (4, 5, 6, 8, 10, 11):                       # warps per CTA of the persistent register-accumulator kernel (D)
+        knob("assemble_variant", 6), knob("assemble_warps", w)
+        res[f"assemble_tangent_force_tmapipe_w{w}_ms"] = timeit(lambda: P.assemble_tangent_force(r["ds"], r["s"], out_k=k, out_f=F))
+    knob("assemble_warps", 0), knob("assemble_variant", 0)
     out["results"] = res
     print(json.dumps(out, indent=1))
 
