@@ -63,6 +63,18 @@ SIGNATURES = {
     "fem_tl_init": [_i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp],
     "fem_tl_update_xr": [_i64, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
     "fem_tl_apply": [_i64, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
+    "fem_mg_sizeof": [_i32],
+    "fem_mg_lattice": [_i64, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "fem_mg_galerkin_fine": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "fem_mg_galerkin_stencil": [_i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
+    "fem_mg_level_finalize": [_i64, _vp, _dbl, _vp, _vp],
+    "fem_mg_stencil_apply": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "fem_mg_stencil_to_dense": [_i32, _i32, _vp, _vp, _vp],
+    "fem_mg_vcycle": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fem_mg_exchange_run": [_vp, _vp, _vp, _vp],
+    "fem_mg_pcg_init": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fem_mg_pcg_update_xr": [_i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "fem_mg_pcg_update_p": [_i64, _vp, _vp, _vp, _i32, _vp],
     "fem_energy_norms": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fem_vec_axpby": [_i64, _dbl, _vp, _dbl, _vp, _vp, _vp],
     "fem_transform": [_vp, _vp, _vp, _vp],

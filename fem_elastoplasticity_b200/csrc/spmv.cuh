@@ -13,11 +13,33 @@ __device__ __forceinline__ double2 ldg_x_keep(const double* x, int m, uint64_t p
   return v;
 }
 
-template <int GROUP, int U>
-__device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __restrict__ nbr_ptr,
+// What happens to the two row sums (K x)_{2a}, (K x)_{2a+1} of node a: called once per node by the first lane of the node's
+// group.  The default stores mask .* (K x) and accumulates x'y; the multigrid smoother (mg.cu) fuses its vector updates here.
+template <bool COHERENT>
+struct SpmvStoreEpilogue {
+  double* __restrict__ y;
+  const uint8_t* __restrict__ mask;
+  const double* x;
+  bool want_dot;
+  __device__ __forceinline__ void operator()(const int64_t a, double acc0, double acc1, double& dot) const {
+    if (mask) {
+      const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
+      if (!mk.x) acc0 = 0.0;
+      if (!mk.y) acc1 = 0.0;
+    }
+    reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
+    if (want_dot) {
+      const double2 xa = COHERENT ? __ldcg(reinterpret_cast<const double2*>(x) + a) : __ldg(reinterpret_cast<const double2*>(x) + a);
+      dot = fma(xa.x, acc0, dot);
+      dot = fma(xa.y, acc1, dot);
+    }
+  }
+};
+
+template <int GROUP, int U, class EPI>
+__device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t* __restrict__ nbr_ptr,
                                             const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
-                                            const double* __restrict__ x, double* __restrict__ y,
-                                            const uint8_t* __restrict__ mask, const bool want_dot) {
+                                            const double* __restrict__ x, const EPI& epi) {
   constexpr int GPW = 32 / GROUP;  // lane groups per warp
   const int lane = threadIdx.x & 31, sub = lane % GROUP, gi = lane / GROUP;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -76,22 +98,19 @@ __device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
       }
       const int64_t a = nb + u * GPW + gi;
-      if (sub == 0 && a < n_n) {
-        if (mask) {
-          const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
-          if (!mk.x) acc0 = 0.0;
-          if (!mk.y) acc1 = 0.0;
-        }
-        reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
-        if (want_dot) {
-          const double2 xa = __ldg(reinterpret_cast<const double2*>(x) + a);
-          dot = fma(xa.x, acc0, dot);
-          dot = fma(xa.y, acc1, dot);
-        }
-      }
+      if (sub == 0 && a < n_n) epi(a, acc0, acc1, dot);
     }
   }
   return dot;
+}
+
+template <int GROUP, int U>
+__device__ __forceinline__ double spmv_rows(const int64_t n_n, const int32_t* __restrict__ nbr_ptr,
+                                            const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
+                                            const double* __restrict__ x, double* __restrict__ y,
+                                            const uint8_t* __restrict__ mask, const bool want_dot) {
+  const SpmvStoreEpilogue<false> epi{y, mask, x, want_dot};
+  return spmv_rows_epi<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, x, epi);
 }
 
 
@@ -144,12 +163,11 @@ __device__ __forceinline__ double2 spmv_ldx(const double* x, int m) {
 }
 
 // blockDim.x == FEM_SPMV_THREADS.  Returns this thread's share of x'y when want_dot.
-template <int GROUP, bool COHERENT>
-__device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
-                                             const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
-                                             const int32_t* __restrict__ tile_seg, const double* __restrict__ vals, const double* x,
-                                             double* __restrict__ y, const uint8_t* __restrict__ mask, const bool want_dot,
-                                             SpmvTileSmem& sm) {
+template <int GROUP, bool COHERENT, class EPI>
+__device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+                                                 const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
+                                                 const int32_t* __restrict__ tile_seg, const double* __restrict__ vals, const double* x,
+                                                 const EPI& epi, SpmvTileSmem& sm) {
   constexpr int U = 2, B = 2;                  // row pairs in flight per lane group, blocks per lane loaded up front
   constexpr int GPC = FEM_SPMV_THREADS / GROUP;  // lane groups per CTA
   constexpr int NPS = GPC * U;                 // nodes per sweep
@@ -236,19 +254,7 @@ __device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_
           acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
         }
         const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
-        if (sub == 0 && a < n_n) {
-          if (mask) {
-            const uchar2 mk = reinterpret_cast<const uchar2*>(mask)[a];
-            if (!mk.x) acc0 = 0.0;
-            if (!mk.y) acc1 = 0.0;
-          }
-          reinterpret_cast<double2*>(y)[a] = make_double2(acc0, acc1);
-          if (want_dot) {
-            const double2 xa = spmv_ldx<COHERENT>(x, (int)a);
-            dot = fma(xa.x, acc0, dot);
-            dot = fma(xa.y, acc1, dot);
-          }
-        }
+        if (sub == 0 && a < n_n) epi(a, acc0, acc1, dot);
       }
     }
     if (staged) {
@@ -258,6 +264,16 @@ __device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_
     __syncthreads();  // xbuf[cur] may be refilled (by the copies for tile it+2, issued at the top of the next iteration)
   }
   return dot;
+}
+
+template <int GROUP, bool COHERENT>
+__device__ __forceinline__ double spmv_tiles(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+                                             const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
+                                             const int32_t* __restrict__ tile_seg, const double* __restrict__ vals, const double* x,
+                                             double* __restrict__ y, const uint8_t* __restrict__ mask, const bool want_dot,
+                                             SpmvTileSmem& sm) {
+  const SpmvStoreEpilogue<COHERENT> epi{y, mask, x, want_dot};
+  return spmv_tiles_epi<GROUP, COHERENT>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, epi, sm);
 }
 
 // lanes per node by block-row length (P1: 7 blocks per row pair -> 2 per lane), nodes in flight, persistent grid size

@@ -38,7 +38,7 @@ class NewtonSolver:
         self.pcg_rtol, self.pcg_maxit, self.check_every = pcg_rtol, pcg_maxit, check_every
         self.refine = refine                               # iterative-refinement steps of the single-GPU Jacobi solve (FemPlan.pcg)
         self.tangent_mode = tangent_mode
-        self.precond, self.coarse_cells, self._tl = precond, coarse_cells, None   # "jacobi" | "twolevel" (see twolevel.py)
+        self.precond, self.coarse_cells, self._tl, self._mg = precond, coarse_cells, None, None   # "jacobi" | "twolevel" (twolevel.py) | "multigrid" (mg.py)
         self.k_elast = plan.assemble_elastic(self.shear, self.bulk)
         self.k_tan = plan.empty(plan.nnz)
         self.E = plan.empty(3, plan.n_int)
@@ -62,6 +62,12 @@ class NewtonSolver:
                 from .twolevel import TwoLevelPCG
                 self._tl = TwoLevelPCG(self.plan, self.mask, nc=self.coarse_cells, part=self.part, free_mask=self.free).setup(self.k_elast)
             x, its, rel = self._tl.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=min(self.check_every, 10))
+            return x.clone(), its, rel
+        if self.precond == "multigrid":                   # V-cycle preconditioner; coarse operators of K_elast, kept (mg.py)
+            if self._mg is None:
+                from .mg import MultigridPCG
+                self._mg = MultigridPCG(self.plan, self.mask, part=self.part, free_mask=self.free).setup(self.k_elast)
+            x, its, rel = self._mg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=min(self.pcg_maxit, 2000), check_every=min(self.check_every, 4))
             return x.clone(), its, rel
         if self._dpcg is not None:                        # ghost rows of the returned vector are current
             x, its = self._dpcg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every)

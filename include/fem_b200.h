@@ -200,6 +200,80 @@ int fem_tl_apply(int64_t n_n, int mode, const double* r, const double* minv, con
                  double y0, double hx, double hy, int ncx, int ncy, const double* zc, double* p, double* scal, int slot, int iter,
                  fem_stream stream);
 
+/* ---- geometric multigrid V-cycle preconditioner (csrc/mg.cu) -------------------------------------------------------------
+ * For meshes whose nodes lie on a uniform lattice (the uniform P1/Q1 meshes of the footing problem and of configs 1/4/5).
+ * Level 0 is the mesh itself (the CSR matrix of the plan); level l >= 1 is a grid of bilinear (Q1) cells of 2^l lattice
+ * steps, stored as a 9-point stencil of 2x2 blocks, S[(4*slot + 2*i + j) * n + node], slot = 3*(dy+1) + (dx+1); the
+ * operators are Galerkin products A_{l+1} = P^T A_l P with P = bilinear interpolation, Dirichlet DOFs masked on level 0.
+ * Smoother: Chebyshev polynomial of `degree` in D^-1 A (point Jacobi), the same before and after the coarse correction,
+ * so the V-cycle is a symmetric positive definite preconditioner for the CG of the Newton step
+ * (replaces the dense LU of Plasticity2D_DP/pythonFEM.py:1062-1066; any SPD preconditioner gives the same solution).
+ * Every transfer is a gather (no atomics): results are bit-reproducible run to run.
+ * Strip partition: a level holds the owned node rows [own_lo, own_hi) plus one ghost row on each side that exists; row 0
+ * of the local arrays is global row g0.  Ghost rows are refreshed by fem_mg_exchange descriptors: peer stores over NVLink
+ * followed by a release flag, and an acquire wait for the neighbours' flags, in ONE small kernel (no library call, CUDA
+ * graph capturable).  On one GPU every exchange is empty.  The host (mg.py) computes the layouts and owns all buffers.   */
+#define FEM_MG_MAX_LEVELS 16
+#define FEM_MG_MAX_DEGREE 8
+#define FEM_MG_MAX_PEERS 16
+typedef struct fem_mg_exchange {
+  int32_t n_send, n_wait;
+  int64_t src_off[FEM_MG_MAX_PEERS]; /* first node (double2) of the rows sent */
+  int64_t count[FEM_MG_MAX_PEERS];   /* nodes sent */
+  double* dst[FEM_MG_MAX_PEERS];     /* destination in the peer's copy of the same vector (peer-mapped address) */
+  uint64_t* dst_flag[FEM_MG_MAX_PEERS];        /* flag word in the peer's communication block raised by this send */
+  const uint64_t* wait_flag[FEM_MG_MAX_PEERS]; /* flag words in this rank's block the sources raise */
+  uint64_t* seq;                     /* this rank: [0] sequence number of the exchange, [1] block ticket */
+} fem_mg_exchange;
+typedef struct fem_mg_level {
+  int32_t nxn, nrows, g0, own_lo, own_hi, nrows_global; /* nodes per row, local rows, global index of local row 0, owned local rows */
+  int32_t res_lo, res_hi;                               /* local rows of b this rank computes by restriction (= owned rows on a
+                                                           distributed level; its share of the rows on the first replicated level) */
+  const double* S;                                      /* [36][nxn*nrows] */
+  const double* dinv;                                   /* [2*nxn*nrows] */
+  double *b, *xa, *xb, *d, *r;                          /* work vectors, [2*nxn*nrows] */
+  double c1[FEM_MG_MAX_DEGREE], c2[FEM_MG_MAX_DEGREE];  /* Chebyshev recurrence d = c1 d + c2 D^-1 r */
+  fem_mg_exchange ex_xa, ex_xb, ex_r, ex_b;             /* ex_b: gather of b to every rank (first replicated level) */
+} fem_mg_level;
+typedef struct fem_mg_desc {
+  int32_t n_levels, degree;          /* structured levels (>= 1); the last one is solved with the dense inverse */
+  int32_t LX, lat_rows, g0, nrows_global; /* level 0: lattice nodes per row, local lattice rows, global index of local row 0 */
+  const int32_t* lat;                /* [lat_rows][LX] lattice point -> node (-1: none) */
+  const int32_t* node_lat;           /* [n_n] node -> lattice point iy_local*LX + ix */
+  int64_t own_node_lo, own_node_hi;  /* nodes of the owned lattice rows (a contiguous id range); ghost nodes are never written */
+  const uint8_t* mask;               /* unknowns of this rank on level 0 (free AND owned) */
+  const double* dinv;                /* level 0: masked inverse diagonal of the CURRENT matrix (fem_jacobi_setup) */
+  double *xa, *xb, *d, *r;           /* level 0 work vectors [n_dof] */
+  double c1[FEM_MG_MAX_DEGREE], c2[FEM_MG_MAX_DEGREE];
+  fem_mg_exchange ex_xa, ex_xb, ex_r;
+  fem_mg_level lev[FEM_MG_MAX_LEVELS]; /* lev[l-1] = level l */
+  const double* coarse_inv;          /* dense inverse of the last level, [n_c][n_c], n_c = 2*nxn*nrows of that level */
+  uint64_t* err;                     /* sticky word: a wait timed out (NULL on one GPU) */
+} fem_mg_desc;
+int fem_mg_sizeof(int which); /* sizeof fem_mg_exchange (0), fem_mg_level (1), fem_mg_desc (2): checked by the binding */
+/* set-up steps (once per mesh / per matrix the hierarchy is built from) */
+int fem_mg_lattice(int64_t n_n, const double* coord, double x0, double y0, double hx, double hy, int LX, int lat_rows, int g0,
+                   int32_t* lat, int32_t* node_lat, int32_t* err, fem_stream stream);
+int fem_mg_galerkin_fine(const fem_plan* plan, const double* K_vals, const uint8_t* row_mask, const uint8_t* col_mask,
+                         const int32_t* node_lat, int LX, int g0, int nxn, int nrows, int g0c, double* S, int32_t* err,
+                         fem_stream stream);
+int fem_mg_galerkin_stencil(int nxf, int nrows_f, int g0f, int nrows_global_f, const double* Sf, int nxc, int nrows_c, int g0c,
+                            int row_lo, int row_hi, double* Sc, fem_stream stream);
+int fem_mg_level_finalize(int64_t n, double* S, double thresh, double* dinv, fem_stream stream);
+int fem_mg_stencil_apply(int nxn, int nrows, int row_lo, int row_hi, const double* S, const double* x, double* y, fem_stream stream);
+int fem_mg_stencil_to_dense(int nxn, int nrows, const double* S, double* A, fem_stream stream);
+/* z = V(r): one V-cycle on the current matrix K_vals (level 0) and the stored coarse operators; if dot != NULL, *dot += r'z
+ * over this rank's unknowns.  r must be zero on masked DOFs.                                         */
+int fem_mg_vcycle(const fem_plan* plan, const fem_mg_desc* desc, const double* K_vals, const double* r, double* z, double* dot,
+                  fem_stream stream);
+int fem_mg_exchange_run(const fem_mg_exchange* ex, double* v, uint64_t* err, fem_stream stream);
+/* CG steps around the V-cycle (scal as in fem_pcg_*: [0]/[2] r'z by iteration parity, [1] r'r, [3] p'Kp, [4] |b|^2):
+ * init: r = mask .* rhs, x = 0, scal zeroed, [1] = [4] = |r|^2;  update_xr: x += alpha p, r -= alpha q, [1] += r'r;
+ * update_p: p = z + beta p (iter < 0: p = z), [3] = 0.                                               */
+int fem_mg_pcg_init(int64_t n, const double* rhs, const uint8_t* mask, double* r, double* x, double* scal, fem_stream stream);
+int fem_mg_pcg_update_xr(int64_t n, const double* p, const double* q, double* x, double* r, double* scal, int iter, fem_stream stream);
+int fem_mg_pcg_update_p(int64_t n, const double* z, double* p, double* scal, int iter, fem_stream stream);
+
 /* energy products for the Newton stopping criterion: out[i] = v_i' K v_i, i < 3 (device double[3], overwritten) */
 int fem_energy_norms(const fem_plan* plan, const double* K_vals, const double* v0, const double* v1, const double* v2,
                      double* work, double* out, fem_stream stream);

@@ -1,0 +1,74 @@
+"""NumPy/SciPy statement of the geometric multigrid V-cycle of fem_elastoplasticity_b200/mg.py + csrc/mg.cu (test helper:
+the reference itself has no iterative solver).  Same hierarchy (every second lattice point, ceil), same
+bilinear transfers, Galerkin operators, unit diagonal on coarse DOFs without free support, Chebyshev-Jacobi smoothing with
+the coefficients of mg.chebyshev_coefficients, dense solve on the last level."""
+import numpy as np
+import scipy.sparse as sp
+
+
+def interp_1d(n_f, n_c):
+    rows, cols, vals = [], [], []
+    for i in range(n_f):
+        if i % 2 == 0:
+            rows.append(i), cols.append(i // 2), vals.append(1.0)
+        else:
+            rows.extend([i, i]), cols.extend([(i - 1) // 2, (i + 1) // 2]), vals.extend([0.5, 0.5])
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n_f, n_c))
+
+
+def prolongation(nxf, nyf):
+    """(2 nxf nyf) x (2 nxc nyc) interpolation between node lattices (node = ix + iy*nx, DOF = 2 node + comp)."""
+    nxc, nyc = -(-(nxf - 1) // 2) + 1, -(-(nyf - 1) // 2) + 1
+    P = sp.kron(interp_1d(nyf, nyc), interp_1d(nxf, nxc), format="csr")
+    return sp.kron(P, sp.identity(2), format="csr"), nxc, nyc
+
+
+class ReferenceMG:
+    def __init__(self, K_setup, q, nx, ny, n_levels, degree, ratio):
+        """K_setup: scipy matrix on the lattice-ordered DOFs; q: free-DOF mask; n_levels structured levels."""
+        self.q = q.astype(float)
+        M = sp.diags(self.q)
+        self.degree, self.ratio = degree, ratio
+        cur = (M @ K_setup @ M).tocsr()
+        self.A, self.P, self.dims = [cur], [], [(nx, ny)]
+        for _ in range(n_levels):
+            P, nx, ny = prolongation(nx, ny)
+            cur = (P.T @ cur @ P).tocsr()                 # the Galerkin chain runs on the raw products ...
+            d = cur.diagonal()
+            Ac = (cur + sp.diags((d <= 1e-14 * d.max()).astype(float))).tocsr()   # ... a level's own dead DOFs get a unit diagonal
+            self.P.append(P), self.A.append(Ac), self.dims.append((nx, ny))
+        self.coarse = np.linalg.inv(self.A[-1].toarray())
+
+    def set_fine(self, K):
+        M = sp.diags(self.q)
+        self.A[0] = (M @ K @ M).tocsr()
+
+    def set_bounds(self, lmax):
+        from fem_elastoplasticity_b200.mg import chebyshev_coefficients
+        self.coef = [chebyshev_coefficients(lm, self.ratio, self.degree) for lm in lmax]
+        self.dinv = []
+        for l, A in enumerate(self.A[:-1]):
+            d = A.diagonal().copy()
+            di = np.where(d != 0, 1.0 / np.where(d != 0, d, 1.0), 0.0)
+            self.dinv.append(di * self.q if l == 0 else di)
+
+    def smooth(self, l, b, x):
+        A, dinv, (c1, c2) = self.A[l], self.dinv[l], self.coef[l]
+        d = np.zeros_like(b)
+        for k in range(self.degree):
+            r = b if x is None else b - A @ x
+            d = (c1[k] * d if k else 0.0) + c2[k] * dinv * r
+            x = d if x is None else x + d
+        return x
+
+    def vcycle(self, b, l=0):
+        if l == len(self.A) - 1:
+            return self.coarse @ b
+        x = self.smooth(l, b, None)
+        r = b - self.A[l] @ x
+        if l == 0:
+            r = r * self.q
+        xc = self.vcycle(self.P[l].T @ r, l + 1)
+        corr = self.P[l] @ xc
+        x = x + (corr * self.q if l == 0 else corr)
+        return self.smooth(l, b, x)

@@ -1,0 +1,136 @@
+"""Geometric multigrid preconditioner (csrc/mg.cu, mg.py): every set-up kernel and the V-cycle against a NumPy/SciPy
+statement of the same algorithm (tests/mg_reference.py), the preconditioned CG against the Jacobi-PCG solution, and the
+Newton drivers with it against the reference traces.  The reference's solve is a dense LU
+(Plasticity2D_DP/pythonFEM.py:1062-1066); any SPD preconditioner yields its solution."""
+import numpy as np
+import pytest
+
+from oracle import fem_oracle as fo
+from mg_reference import ReferenceMG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fem():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from fem_elastoplasticity_b200 import meshgen, mg, plan
+    return {"torch": torch, "plan": plan, "mg": mg, "meshgen": meshgen}
+
+
+def p1_tables():
+    xi, wf = fo.quadrature_volume(fo.ElementType.P1)
+    _, d1, d2 = fo.local_basis_volume(fo.ElementType.P1, xi)
+    return d1, d2, wf
+
+
+def stencil_to_scipy(S, nxn, nrows):
+    import scipy.sparse as sp
+    n = nxn * nrows
+    S = S.reshape(9, 4, nrows, nxn)
+    rows, cols, vals = [], [], []
+    jj, ii = np.meshgrid(np.arange(nrows), np.arange(nxn), indexing="ij")
+    for s in range(9):
+        dx, dy = s % 3 - 1, s // 3 - 1
+        ok = (ii + dx >= 0) & (ii + dx < nxn) & (jj + dy >= 0) & (jj + dy < nrows)
+        node, nb = (ii + jj * nxn)[ok], (ii + dx + (jj + dy) * nxn)[ok]
+        for q in range(4):
+            rows.append(2 * node + q // 2), cols.append(2 * nb + q % 2), vals.append(S[s, q][ok])
+        assert not S[s][:, ~ok].any()                      # nothing stored towards neighbours that do not exist
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(2 * n, 2 * n))
+
+
+@pytest.mark.parametrize("nx,ny", [(37, 21), (64, 48)])
+def test_hierarchy_and_vcycle_match_numpy_statement(fem, nx, ny):
+    torch, mg = fem["torch"], fem["mg"]
+    d1, d2, wf = p1_tables()
+    m = fem["meshgen"].square_mesh_p1(nx, ny, 10.0, 10.0 * ny / nx)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    G, Kb, eta, c = fem["meshgen"].footing_materials(P.n_int)
+    k_el = P.assemble_elastic(G, Kb)
+    from fem_elastoplasticity_b200.plan import dp_return_map
+    r = dp_return_map(fem["meshgen"].synthetic_strain(P.n_int), None, G, Kb, eta, c)
+    k_tan = P.assemble_tangent(r["ds"])
+    mask = P.mask_u8(m["Q"])
+    M = mg.MultigridPCG(P, mask, degree=3, ratio=8.0, max_coarse_dofs=120).setup(k_el)
+    assert M.n_levels >= 3
+    q = mask.cpu().numpy().astype(bool)
+    Kel, Ktan = P.to_scipy_csr(k_el), P.to_scipy_csr(k_tan)
+    ref = ReferenceMG(Kel, q, nx + 1, ny + 1, M.n_levels, 3, 8.0)
+    for li, lv in enumerate(M.lv):
+        assert (lv["nxn"], lv["nrows"]) == ref.dims[li + 1]
+        got = stencil_to_scipy(lv["S"].cpu().numpy(), lv["nxn"], lv["nrows"])
+        want = ref.A[li + 1]
+        assert abs(got - want).max() <= 1e-12 * abs(want).max(), li
+        d = want.diagonal()
+        np.testing.assert_allclose(lv["dinv"].cpu().numpy(), 1.0 / d, rtol=1e-12)
+    # eigenvalue bounds: power iteration underestimates, never above the true lambda_max by more than the 1.1 margin
+    import scipy.sparse.linalg as spla
+    for l, lm in enumerate([M.lmax0] + [lv["lmax"] for lv in M.lv[:-1]]):
+        A = ref.A[l]
+        d = A.diagonal()
+        di = np.where(d != 0, 1.0 / np.where(d != 0, d, 1.0), 0.0)
+        true = spla.eigs(spla.LinearOperator(A.shape, matvec=lambda v: di * (A @ v)), k=1, which="LM", return_eigenvectors=False, tol=1e-6)[0].real
+        assert 0.9 * true <= lm <= 1.12 * true, (l, lm, true)
+    # one V-cycle on the tangent matrix (coarse operators of K_elast) against the NumPy statement
+    ref.set_fine(Ktan)
+    ref.set_bounds([M.lmax0] + [lv["lmax"] for lv in M.lv[:-1]])
+    P.jacobi(k_tan, mask, out=M.minv)
+    rng = np.random.default_rng(3)
+    rv = rng.standard_normal(P.n_dof) * q
+    z = torch.zeros(P.n_dof, dtype=torch.float64, device="cuda")
+    dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    M.vcycle(k_tan, torch.as_tensor(rv).cuda(), z, dot)
+    zr = ref.vcycle(rv)
+    np.testing.assert_allclose(z.cpu().numpy(), zr, rtol=0, atol=1e-11 * np.abs(zr).max())
+    assert abs(float(dot.item()) - rv @ zr) <= 1e-11 * abs(rv @ zr)
+    # the V-cycle is symmetric: u'M(v) == v'M(u)
+    uv = rng.standard_normal(P.n_dof) * q
+    assert abs(uv @ zr - rv @ ref.vcycle(uv)) <= 1e-10 * abs(uv @ zr)
+
+
+def test_multigrid_pcg_solves_the_newton_system(fem):
+    """CG + V-cycle on K_tangent[Q,Q] x = -F[Q] (synthetic plastic state, coarse operators of K_elast): same solution as
+    Jacobi-PCG, h-independent iteration count, graph replay == eager launches."""
+    torch, mg = fem["torch"], fem["mg"]
+    from fem_elastoplasticity_b200.plan import dp_return_map
+    d1, d2, wf = p1_tables()
+    its = {}
+    for nx in (96, 384):
+        m = fem["meshgen"].square_mesh_p1(nx, nx)
+        P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+        G, Kb, eta, c = fem["meshgen"].footing_materials(P.n_int)
+        k_el = P.assemble_elastic(G, Kb)
+        r = dp_return_map(fem["meshgen"].synthetic_strain(P.n_int), None, G, Kb, eta, c)
+        k_tan, F = P.assemble_tangent_force(r["ds"], r["s"])
+        mask = P.mask_u8(m["Q"])
+        M = mg.MultigridPCG(P, mask).setup(k_el)
+        x, n_it, rel = M.solve(k_tan, -F, rtol=1e-10)
+        x = x.clone()
+        true = float(((-F - P.spmv(k_tan, x)) * mask).norm() / (F * mask).norm())
+        assert rel <= 1e-10 and true <= 2e-10, (rel, true)
+        xj, _, _ = P.pcg(k_tan, -F, mask, rtol=1e-12, maxit=200000)
+        assert float((x - xj).abs().max() / xj.abs().max()) <= 1e-7
+        its[nx] = n_it
+        M.use_graph = False
+        x2, n2, _ = M.solve(k_tan, -F, rtol=1e-10)
+        assert n2 == n_it and float((x2 - x).abs().max()) <= 1e-9 * float(x.abs().max())
+    print("multigrid PCG iterations:", its)
+    assert max(its.values()) <= 60 and its[384] <= its[96] + 8
+
+
+def test_newton_drivers_with_multigrid(golden):
+    """Footing load stepping with the multigrid-preconditioned solve: the reference's level-1 trace (109 Newton iterations,
+    16 steps) and the dense-LU displacements."""
+    from fem_elastoplasticity_b200 import newton
+    f = golden("assembly_footing_p1_l1.npz")
+    mesh = {k: f[k] for k in ("coordinates", "elements", "Q", "dirichlet_nodes")}
+    out = newton.footing_driver(mesh, pcg_rtol=1e-13, precond="multigrid")
+    oref = fo.footing_driver(1)
+    assert len(out["trace"]) == len(oref["trace"]) == 109
+    assert [t[2] for t in out["trace"]] == [t[2] for t in oref["trace"]]
+    err = np.abs(out["U"] - oref["U"]).max() / np.abs(oref["U"]).max()
+    print("footing L1 with multigrid: displacement error vs dense-LU oracle", err, "PCG iterations", [t[4] for t in out["trace"]][:8])
+    assert err <= 1e-9
