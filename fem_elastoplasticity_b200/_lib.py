@@ -71,6 +71,8 @@ SIGNATURES = {
     "fem_mg_stencil_apply": [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "fem_mg_stencil_to_dense": [_i32, _i32, _vp, _vp, _vp],
     "fem_mg_vcycle": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fem_peer_allreduce": [_vp, _i32, _vp, C.POINTER(_vp), _i64, _i64, _i64, _i32, _i32, _vp],
+    "fem_mg_to_f32": [_i64, _vp, _vp, _vp],
     "fem_mg_exchange_run": [_vp, _vp, _vp, _vp],
     "fem_mg_pcg_init": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "fem_mg_pcg_update_xr": [_i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
@@ -78,6 +80,8 @@ SIGNATURES = {
     "fem_energy_norms": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fem_vec_axpby": [_i64, _dbl, _vp, _dbl, _vp, _vp, _vp],
     "fem_transform": [_vp, _vp, _vp, _vp],
+    "fem_vector_volume": [_vp, _vp, C.POINTER(_dbl), _vp, _vp],
+    "fem_segment_sum_ordered": [_i64, _vp, _vp, _vp, _vp],
     "fem_set_tuning": [C.c_char_p, _i32],
 }
 _RESTYPE = {"fem_last_error_string": C.c_char_p, "fem_plan_bytes": _i64}

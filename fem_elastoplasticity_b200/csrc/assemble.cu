@@ -1145,6 +1145,63 @@ __global__ void __launch_bounds__(256) strain_kernel(int64_t n_e, const int32_t*
   }
 }
 
+// P1 (one integration point per element): the three gradients are recomputed from the node coordinates with the
+// operations of geometry_kernel (plan.cu) in the same order, so they are the stored values bit for bit - and the kernel
+// moves 12 B of node ids + two 16-byte gathers per node (served by L1/L2: a node is shared by six elements) instead of
+// streaming 48 B of stored gradients per element: compulsory traffic 12 + 8 + 8 + 24 B/element.  Measured at 16M elements:
+// 0.308 ms against 0.221 ms of the stored-gradient kernel - six more 16-byte gathers per element cost more in L2 than the
+// 48 streamed bytes cost in HBM - so it is NOT the default (tuning key strain_variant = 2 selects it; tested bit-identical).
+__global__ void __launch_bounds__(256) strain_p1_kernel(int64_t n_e, FemRefElem ref, const int32_t* __restrict__ elem,
+                                                        const double2* __restrict__ coord2, const double* __restrict__ u,
+                                                        double* __restrict__ E) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_e; g += (int64_t)gridDim.x * blockDim.x) {
+    int32_t nd[3];
+    int pp[3];
+    double a1[3], a2[3];
+    double j11 = 0.0, j12 = 0.0, j21 = 0.0, j22 = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      nd[p] = __ldcs(elem + (int64_t)p * n_e + g);
+      pp[p] = p;
+      const double2 c = __ldg(coord2 + nd[p]);
+      const double h1 = ref.dhat1[p], h2 = ref.dhat2[p];
+      j11 = j11 + c.x * h1;
+      j12 = j12 + c.y * h1;
+      j21 = j21 + c.x * h2;
+      j22 = j22 + c.y * h2;
+    }
+    const double det = j11 * j22 - j12 * j21;
+    const double i11 = j22 / det, i12 = -j12 / det, i21 = -j21 / det, i22 = j11 / det;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const double h1 = ref.dhat1[p], h2 = ref.dhat2[p];
+      a1[p] = i11 * h1 + i12 * h2;
+      a2[p] = i21 * h1 + i22 * h2;
+    }
+#pragma unroll
+    for (int i = 1; i < 3; ++i)  // ascending node id: csr_matvec order (see strain_kernel)
+#pragma unroll
+      for (int j = i; j > 0; --j)
+        if (nd[j - 1] > nd[j]) {
+          const int32_t tn = nd[j]; nd[j] = nd[j - 1]; nd[j - 1] = tn;
+          const int tp = pp[j]; pp[j] = pp[j - 1]; pp[j - 1] = tp;
+        }
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const double2 uv = __ldg(reinterpret_cast<const double2*>(u) + nd[s]);
+      const double b1 = pp[s] == 0 ? a1[0] : (pp[s] == 1 ? a1[1] : a1[2]);
+      const double b2 = pp[s] == 0 ? a2[0] : (pp[s] == 1 ? a2[1] : a2[2]);
+      e0 = e0 + b1 * uv.x;
+      e1 = e1 + b2 * uv.y;
+      e2 = (e2 + b2 * uv.x) + b1 * uv.y;
+    }
+    __stcs(E + g, e0);
+    __stcs(E + n_e + g, e1);
+    __stcs(E + 2 * n_e + g, e2);
+  }
+}
+
 extern "C" int fem_strain(const fem_plan* P, const double* u, double* E, fem_stream stream) {
   FEM_REQUIRE(P && u && E, "null pointer");
   FEM_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15u) == 0, "u must be 16-byte aligned");
@@ -1154,8 +1211,10 @@ extern "C" int fem_strain(const fem_plan* P, const double* u, double* E, fem_str
   const unsigned blocks = (unsigned)b;
   cudaStream_t st = (cudaStream_t)stream;
 #define STRAIN(NP, NQ) strain_kernel<NP, NQ><<<blocks, threads, 0, st>>>(P->n_e, P->elem, P->dphi1, P->dphi2, u, E)
-  if (P->n_p == 3 && P->n_q == 1) STRAIN(3, 1);
-  else if (P->n_p == 6 && P->n_q == 7) STRAIN(6, 7);
+  if (P->n_p == 3 && P->n_q == 1) {
+    if (P->coord2 && g_fem_tuning.strain_variant == 2) strain_p1_kernel<<<blocks, threads, 0, st>>>(P->n_e, P->ref, P->elem, P->coord2, u, E);
+    else STRAIN(3, 1);
+  } else if (P->n_p == 6 && P->n_q == 7) STRAIN(6, 7);
   else if (P->n_p == 4 && P->n_q == 4) STRAIN(4, 4);
   else if (P->n_p == 8 && P->n_q == 9) STRAIN(8, 9);
   else {
@@ -1196,6 +1255,70 @@ extern "C" int fem_transform(const fem_plan* P, const double* q_int, double* q_n
   const int threads = 128;
   transform_kernel<<<(unsigned)fem_div_up(P->n_slices * 32, threads), threads, 0, (cudaStream_t)stream>>>(
       P->n_n, P->n_slices, P->n_q, P->slice_ptr, P->inc_key, P->weight, q_int, q_node);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+// ---- load vectors of the linear-elastic demo (Elasticity2D/pythonFEM.py:246-364) ---------------------------------------
+// Volume forces: f_V[c, n] = sum over the integration points g = e*n_q + q of the elements around node n (ascending g) of
+// hatp[la, q] * (weight[g] * f[c, g]) - the order in which SciPy sums the reference's COO triplets (:281-290), so the
+// result is bit-identical.  Same walk of the node's incidence list as transform_kernel; no atomics.
+struct HatTable { double h[FEM_MAX_NP * FEM_MAX_NQ]; };  // (n_p, n_q) row-major
+__global__ void vector_volume_kernel(int64_t n_n, int64_t n_slices, int n_q, int64_t n_int, const int64_t* __restrict__ slice_ptr,
+                                     const uint32_t* __restrict__ inc_key, const double* __restrict__ weight, const HatTable hat,
+                                     const double* __restrict__ f_int, double* __restrict__ out) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t slice = a >> 5;
+  if (slice >= n_slices) return;
+  const int lane = (int)(a & 31);
+  const int64_t sbase = slice_ptr[slice];
+  const int width = (int)((slice_ptr[slice + 1] - sbase) >> 5);
+  double f0 = 0.0, f1 = 0.0;
+  for (int i = 0; i < width; ++i) {
+    const uint32_t key = inc_key[sbase + (int64_t)i * 32 + lane];
+    if (key == FEM_INVALID_KEY) continue;
+    const int64_t e = key >> 3;
+    const int la = (int)(key & 7u);
+    for (int q = 0; q < n_q; ++q) {
+      const int64_t g = e * n_q + q;
+      const double w = weight[g], hp = hat.h[la * n_q + q];
+      f0 = f0 + hp * (w * f_int[g]);
+      f1 = f1 + hp * (w * f_int[n_int + g]);
+    }
+  }
+  if (a < n_n) {
+    out[a] = f0;
+    out[n_n + a] = f1;
+  }
+}
+
+extern "C" int fem_vector_volume(const fem_plan* P, const double* f_int, const double* h_hatp, double* out, fem_stream stream) {
+  FEM_REQUIRE(P && f_int && h_hatp && out, "null pointer");
+  HatTable hat;
+  memset(&hat, 0, sizeof(hat));
+  for (int i = 0; i < P->n_p * P->n_q; ++i) hat.h[i] = h_hatp[i];
+  const int threads = 128;
+  vector_volume_kernel<<<(unsigned)fem_div_up(P->n_slices * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      P->n_n, P->n_slices, P->n_q, P->n_int, P->slice_ptr, P->inc_key, P->weight, hat, f_int, out);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
+// out[s] = ((0 + v[ptr[s]]) + v[ptr[s]+1]) + ... : the sequential sum of every segment, one thread per segment.  With the
+// contributions stably sorted by target node this is SciPy's duplicate summation of COO triplets in input order
+// (surface tractions, :327-362: the boundary mesh has no incidence lists in the plan).
+__global__ void segment_sum_ordered_kernel(int64_t n_seg, const int64_t* __restrict__ ptr, const double* __restrict__ v, double* __restrict__ out) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_seg; s += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int64_t i = ptr[s]; i < ptr[s + 1]; ++i) acc = acc + v[i];
+    out[s] = acc;
+  }
+}
+
+extern "C" int fem_segment_sum_ordered(int64_t n_seg, const int64_t* seg_ptr, const double* vals, double* out, fem_stream stream) {
+  FEM_REQUIRE(seg_ptr && out && n_seg >= 0, "null pointer");
+  if (n_seg == 0) return FEM_OK;
+  segment_sum_ordered_kernel<<<(unsigned)fem_div_up(n_seg, 256), 256, 0, (cudaStream_t)stream>>>(n_seg, seg_ptr, vals, out);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

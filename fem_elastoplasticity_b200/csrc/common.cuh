@@ -35,6 +35,7 @@ struct FemTuning {
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
   int spmv_staged;         // 0 auto (staged x when the plan has tiles), 1 gather x from global memory (round-1 kernel)
   int peer_timeout_ms;     // bound of the in-kernel waits of the fused multi-GPU PCG (0 = 10 000 ms)
+  int strain_variant;      // 0/1 stored gradients (default), 2 P1 gradients recomputed from the coordinates (slower: L2 gathers)
   int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
 };
 extern FemTuning g_fem_tuning;
@@ -86,6 +87,7 @@ struct fem_plan {
   double* dphi1;   // [n_p][n_int]
   double* dphi2;   // [n_p][n_int]
   double* weight;  // [n_int]
+  double2* coord2;  // [n_n] node coordinates (x, y) interleaved: one 16-byte gather per node (P1 strain kernel)
   // scratch
   double* dscratch;  // small device scratch: 8 doubles (PCG scalars) + FEM_SLICE_COUNTERS 8-byte counters
   // TMA staging data of the P1 assembly kernel (valid when stage_ok): per 32-node slice the touched elements as

@@ -11,6 +11,10 @@
 #include "spmv.cuh"
 #include "peer.cuh"
 
+struct fem_peer_table {
+  void* p[FEM_MG_MAX_PEERS];
+};
+
 namespace {
 
 struct Geom {  // local part of one structured level
@@ -264,26 +268,26 @@ struct MgFineEpilogue {
   }
 };
 
-template <int GROUP, int MODE>
+template <int GROUP, int MODE, class VT>
 __global__ void __launch_bounds__(FEM_SPMV_THREADS) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
-                                                                         const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
+                                                                         const int32_t* __restrict__ tile_seg, const VT* __restrict__ vals,
                                                                          const double* x, const MgFineEpilogue<MODE> epi, double* dot_out) {
   __shared__ double red[32];
   __shared__ SpmvTileSmem sm;
-  double dot = spmv_tiles_epi<GROUP, false>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, epi, sm);
+  double dot = spmv_tiles_epi<GROUP, false, MgFineEpilogue<MODE>, VT>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, epi, sm);
   if (dot_out) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) atomicAdd(dot_out, dot);
   }
 }
 
-template <int GROUP, int MODE>
+template <int GROUP, int MODE, class VT>
 __global__ void __launch_bounds__(256) mg_fine_rows_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
-                                                           const double* __restrict__ vals, const double* __restrict__ x,
+                                                           const VT* __restrict__ vals, const double* __restrict__ x,
                                                            const MgFineEpilogue<MODE> epi, double* dot_out) {
   __shared__ double red[32];
-  double dot = spmv_rows_epi<GROUP, 2>(n_n, nbr_ptr, nbr_idx, vals, x, epi);
+  double dot = spmv_rows_epi<GROUP, 2, MgFineEpilogue<MODE>, VT>(n_n, nbr_ptr, nbr_idx, vals, x, epi);
   if (dot_out) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) atomicAdd(dot_out, dot);
@@ -405,6 +409,33 @@ __global__ void __launch_bounds__(256) mg_exchange_kernel(const fem_mg_exchange 
   }
 }
 
+// ---- sum of a few scalars over all ranks through peer memory (the CG's dot products): every rank stores its values as
+// self-validating 16-byte lines into every rank's block, polls its own block for all ranks' lines and adds them in rank
+// order (bit-identical result everywhere).  Lines are double-buffered by the parity of the sequence number: a rank can
+// only be one all-reduce ahead of any other, since finishing one needs everybody's lines of that one. ----
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(double* vals, int n, uint64_t* local, const fem_peer_table peers, int64_t lines_off,
+                                                             int64_t seq_off, int64_t err_off, int rank, int world, uint64_t timeout_ns) {
+  __shared__ double sh[FEM_MG_MAX_PEERS][8];
+  const uint32_t seq = (uint32_t)local[seq_off] + 1u;
+  const int par = (int)(seq & 1u), t = threadIdx.x;
+  if (t < world * n) {
+    const int r = t / n, i = t % n;
+    uint64_t* dst = reinterpret_cast<uint64_t*>(peers.p[r]) + lines_off + (int64_t)(((par * FEM_MG_MAX_PEERS + rank) * 8 + i) * 2);
+    line_store(dst, vals[i], seq);
+  }
+  if (t < world * n) {
+    const int r = t / n, i = t % n;
+    sh[r][i] = line_wait(local + lines_off + (int64_t)(((par * FEM_MG_MAX_PEERS + r) * 8 + i) * 2), seq, local + err_off, 0, timeout_ns);
+  }
+  __syncthreads();
+  if (t < n) {
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += sh[r][t];
+    vals[t] = acc;
+  }
+  if (t == 0) local[seq_off] = seq;
+}
+
 // ---- CG steps around the V-cycle --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mg_pcg_init_kernel(int64_t n, const double* __restrict__ rhs, const uint8_t* __restrict__ mask,
                                                           double* __restrict__ r, double* __restrict__ x, double* scal) {
@@ -504,22 +535,22 @@ int launch_stencil(const fem_mg_level& L, const double* x, double* out, double c
   return FEM_OK;
 }
 
-template <int MODE>
-int launch_fine(const fem_plan* P, const fem_mg_desc* D, const double* K, const double* b, const double* x, double* out, double c1, double c2,
-                double* dot, cudaStream_t st) {
+template <int MODE, class VT>
+int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const double* b, const double* x, double* out, double c1, double c2,
+                   double* dot, cudaStream_t st) {
   MgFineEpilogue<MODE> epi{reinterpret_cast<const double2*>(b), reinterpret_cast<const double2*>(D->dinv), reinterpret_cast<double2*>(D->d),
                            reinterpret_cast<const double2*>(x), reinterpret_cast<double2*>(out), D->mask, c1, c2, dot != nullptr,
                            D->own_node_lo, D->own_node_hi};
   const SpmvShape sh = spmv_shape(P);
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
-#define MGT(G) mg_fine_tiles_kernel<G, MODE><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot)
+#define MGT(G) mg_fine_tiles_kernel<G, MODE, VT><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot)
     if (sh.group == 4) MGT(4);
     else if (sh.group == 8) MGT(8);
     else MGT(16);
 #undef MGT
   } else {
-#define MGR(G) mg_fine_rows_kernel<G, MODE><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K, x, epi, dot)
+#define MGR(G) mg_fine_rows_kernel<G, MODE, VT><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K, x, epi, dot)
     if (sh.group == 4) MGR(4);
     else if (sh.group == 8) MGR(8);
     else MGR(16);
@@ -527,6 +558,21 @@ int launch_fine(const fem_plan* P, const fem_mg_desc* D, const double* K, const 
   }
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
+}
+
+// level-0 step on the FP32 copy of the matrix when the descriptor carries one (smoother and residual of the V-cycle only)
+template <int MODE>
+int launch_fine(const fem_plan* P, const fem_mg_desc* D, const double* K, const double* b, const double* x, double* out, double c1, double c2,
+                double* dot, cudaStream_t st) {
+  if (D->K32) return launch_fine_vt<MODE, float>(P, D, D->K32, b, x, out, c1, c2, dot, st);
+  return launch_fine_vt<MODE, double>(P, D, K, b, x, out, c1, c2, dot, st);
+}
+
+__global__ void __launch_bounds__(256) mg_to_f32_kernel(int64_t n4, const double4* __restrict__ src, float4* __restrict__ dst) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 a = __ldcs(reinterpret_cast<const double2*>(src + i)), b = __ldcs(reinterpret_cast<const double2*>(src + i) + 1);
+    __stcs(dst + i, make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y));
+  }
 }
 
 #define MG_TRY(expr)             \
@@ -658,9 +704,30 @@ extern "C" int fem_mg_stencil_to_dense(int nxn, int nrows, const double* S, doub
   return FEM_OK;
 }
 
+extern "C" int fem_mg_to_f32(int64_t n, const double* src, float* dst, fem_stream stream) {
+  FEM_REQUIRE(src && dst && n > 0 && n % 4 == 0, "null pointer or length not a multiple of 4");
+  FEM_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "16-byte alignment");
+  mg_to_f32_kernel<<<vgrid(n / 4, 0) * 4, 256, 0, (cudaStream_t)stream>>>(n / 4, reinterpret_cast<const double4*>(src), reinterpret_cast<float4*>(dst));
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
+}
+
 extern "C" int fem_mg_exchange_run(const fem_mg_exchange* ex, double* v, uint64_t* err, fem_stream stream) {
   FEM_REQUIRE(ex && v, "null pointer");
   return run_exchange(*ex, v, err, (cudaStream_t)stream);
+}
+
+extern "C" int fem_peer_allreduce(double* vals, int n, void* comm, const void* const* peers, int64_t lines_word, int64_t seq_word,
+                                  int64_t err_word, int rank, int world, fem_stream stream) {
+  FEM_REQUIRE(vals && comm && peers && n >= 1 && n <= 8 && world >= 1 && world <= FEM_MG_MAX_PEERS && rank >= 0 && rank < world, "arguments");
+  fem_peer_table tab;
+  for (int r = 0; r < FEM_MG_MAX_PEERS; ++r) tab.p[r] = r < world ? const_cast<void*>(peers[r]) : nullptr;
+  tab.p[rank] = comm;
+  const uint64_t timeout_ns = (uint64_t)(g_fem_tuning.peer_timeout_ms > 0 ? g_fem_tuning.peer_timeout_ms : 10000) * 1000000ull;
+  peer_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(vals, n, reinterpret_cast<uint64_t*>(comm), tab, lines_word, seq_word, err_word, rank, world,
+                                                            timeout_ns);
+  FEM_CUDA_CHECK(cudaGetLastError());
+  return FEM_OK;
 }
 
 extern "C" int fem_mg_vcycle(const fem_plan* P, const fem_mg_desc* D, const double* K_vals, const double* r, double* z, double* dot,

@@ -31,6 +31,7 @@ extern "C" int fem_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "spmv_staged")) g_fem_tuning.spmv_staged = value;
   else if (!strcmp(key, "peer_timeout_ms")) g_fem_tuning.peer_timeout_ms = value;
   else if (!strcmp(key, "peer_nowait")) g_fem_tuning.peer_nowait = value;
+  else if (!strcmp(key, "strain_variant")) g_fem_tuning.strain_variant = value;
   else {
     fem_set_error("unknown tuning key %s", key);
     return FEM_ERR_INVALID_ARG;
@@ -570,6 +571,11 @@ static int dmalloc(fem_plan* p, T** ptr, int64_t count) {
     if (_rc != FEM_OK) return _rc; \
   } while (0)
 
+__global__ void interleave_coord(int64_t n_n, const double* __restrict__ coord, double2* __restrict__ out) {
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_n; a += (int64_t)gridDim.x * blockDim.x)
+    out[a] = make_double2(coord[a], coord[n_n + a]);
+}
+
 static int launch_geometry(fem_plan* P, const double* coord, int* d_bad, cudaStream_t st) {
   const int threads = 256;
   const unsigned blocks = (unsigned)fem_div_up(P->n_int, threads);
@@ -688,6 +694,8 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     P->dphi2 = P->geom + (int64_t)(1 + n_p) * P->n_int;
     if ((rc = dmalloc(P, &P->dscratch, 8 + FEM_SLICE_COUNTERS)) != FEM_OK) break;
     if ((rc = launch_geometry(P, coord, flags + 3, st)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->coord2, n_n)) != FEM_OK) break;
+    interleave_coord<<<grid(n_n), threads, 0, st>>>(n_n, coord, P->coord2);
     // TMA staging plan (P1 meshes of bounded valence whose slices touch few runs of consecutive elements)
     P->stage_ok = 0;
     if (n_p == 3 && P->n_q == 1 && P->max_degree <= 8 && P->max_inc <= 8 && (P->n_int % 2) == 0 && P->n_int >= 64) {
@@ -782,7 +790,7 @@ extern "C" int fem_plan_destroy(fem_plan* P) {
   cudaFree(P->stage_box); cudaFree(P->inc_stage); cudaFree(P->tile_seg); cudaFree(P->nbr_loc);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
-  cudaFree(P->geom); cudaFree(P->dscratch);
+  cudaFree(P->geom); cudaFree(P->dscratch); cudaFree(P->coord2);
   delete P;
   return FEM_OK;
 }

@@ -13,6 +13,18 @@ __device__ __forceinline__ double2 ldg_x_keep(const double* x, int m, uint64_t p
   return v;
 }
 
+// Matrix values are FP64 (the operator of the CG) or FP32 (the copy the multigrid smoother streams: a preconditioner
+// only needs a fixed symmetric approximation, and the SpMV is bound by the bytes of the values).  Products and sums are
+// FP64 either way.
+template <class VT> struct SpmvPair;
+template <> struct SpmvPair<double> { using type = double2; };
+template <> struct SpmvPair<float> { using type = float2; };
+template <class VT>
+__device__ __forceinline__ double2 spmv_ld_pair(const typename SpmvPair<VT>::type* p) {
+  const typename SpmvPair<VT>::type v = __ldcs(p);
+  return make_double2((double)v.x, (double)v.y);
+}
+
 // What happens to the two row sums (K x)_{2a}, (K x)_{2a+1} of node a: called once per node by the first lane of the node's
 // group.  The default stores mask .* (K x) and accumulates x'y; the multigrid smoother (mg.cu) fuses its vector updates here.
 template <bool COHERENT>
@@ -36,9 +48,9 @@ struct SpmvStoreEpilogue {
   }
 };
 
-template <int GROUP, int U, class EPI>
+template <int GROUP, int U, class EPI, class VT = double>
 __device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t* __restrict__ nbr_ptr,
-                                            const int32_t* __restrict__ nbr_idx, const double* __restrict__ vals,
+                                            const int32_t* __restrict__ nbr_idx, const VT* __restrict__ vals,
                                             const double* __restrict__ x, const EPI& epi) {
   constexpr int GPW = 32 / GROUP;  // lane groups per warp
   const int lane = threadIdx.x & 31, sub = lane % GROUP, gi = lane / GROUP;
@@ -67,10 +79,11 @@ __device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t
       m[u] = 0;
       v0[u] = v1[u] = make_double2(0.0, 0.0);
       if (sub < deg[u]) {
-        const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
+        using P2 = typename SpmvPair<VT>::type;
+        const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
         m[u] = __ldg(nbr_idx + p0[u] + sub);
-        v0[u] = __ldcs(row0 + sub);
-        v1[u] = __ldcs(row0 + deg[u] + sub);
+        v0[u] = spmv_ld_pair<VT>(row0 + sub);
+        v1[u] = spmv_ld_pair<VT>(row0 + deg[u] + sub);
       }
     }
 #pragma unroll
@@ -83,9 +96,10 @@ __device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t
       double acc0 = fma(v0[u].y, xv[u].y, v0[u].x * xv[u].x);
       double acc1 = fma(v1[u].y, xv[u].y, v1[u].x * xv[u].x);
       for (int j = sub + GROUP; j < deg[u]; j += GROUP) {  // rows longer than GROUP blocks
-        const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
+        using P2 = typename SpmvPair<VT>::type;
+        const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
         const int mm = __ldg(nbr_idx + p0[u] + j);
-        const double2 w0 = __ldcs(row0 + j), w1 = __ldcs(row0 + deg[u] + j);
+        const double2 w0 = spmv_ld_pair<VT>(row0 + j), w1 = spmv_ld_pair<VT>(row0 + deg[u] + j);
         const double2 xx = ldg_x_keep(x, mm, pol);
         acc0 = fma(w0.x, xx.x, acc0);
         acc0 = fma(w0.y, xx.y, acc0);
@@ -163,10 +177,10 @@ __device__ __forceinline__ double2 spmv_ldx(const double* x, int m) {
 }
 
 // blockDim.x == FEM_SPMV_THREADS.  Returns this thread's share of x'y when want_dot.
-template <int GROUP, bool COHERENT, class EPI>
+template <int GROUP, bool COHERENT, class EPI, class VT = double>
 __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                  const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
-                                                 const int32_t* __restrict__ tile_seg, const double* __restrict__ vals, const double* x,
+                                                 const int32_t* __restrict__ tile_seg, const VT* __restrict__ vals, const double* x,
                                                  const EPI& epi, SpmvTileSmem& sm) {
   constexpr int U = 2, B = 2;                  // row pairs in flight per lane group, blocks per lane loaded up front
   constexpr int GPC = FEM_SPMV_THREADS / GROUP;  // lane groups per CTA
@@ -215,10 +229,11 @@ __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_
           m[u][b] = 0;
           v0[u][b] = v1[u][b] = make_double2(0.0, 0.0);
           if (j < deg[u]) {
-            const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
+            using P2 = typename SpmvPair<VT>::type;
+            const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
             m[u][b] = staged ? (int)__ldcs(nbr_loc + p0[u] + j) : __ldg(nbr_idx + p0[u] + j);
-            v0[u][b] = __ldcs(row0 + j);
-            v1[u][b] = __ldcs(row0 + deg[u] + j);
+            v0[u][b] = spmv_ld_pair<VT>(row0 + j);
+            v1[u][b] = spmv_ld_pair<VT>(row0 + deg[u] + j);
           }
         }
       if (staged && !waited) {  // the matrix values above are in flight while the x ranges arrive
@@ -240,8 +255,9 @@ __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_
           }
         }
         for (int j = sub + B * GROUP; j < deg[u]; j += GROUP) {  // rows longer than B*GROUP blocks
-          const double2* row0 = reinterpret_cast<const double2*>(vals + 4 * (int64_t)p0[u]);
-          const double2 w0 = __ldcs(row0 + j), w1 = __ldcs(row0 + deg[u] + j);
+          using P2 = typename SpmvPair<VT>::type;
+          const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
+          const double2 w0 = spmv_ld_pair<VT>(row0 + j), w1 = spmv_ld_pair<VT>(row0 + deg[u] + j);
           const double2 xx = staged ? xs[__ldcs(nbr_loc + p0[u] + j)] : spmv_ldx<COHERENT>(x, __ldg(nbr_idx + p0[u] + j));
           acc0 = fma(w0.x, xx.x, acc0);
           acc0 = fma(w0.y, xx.y, acc0);

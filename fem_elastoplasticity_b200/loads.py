@@ -12,6 +12,16 @@ def _scatter_ordered(vals, nodes, n_n):
     order = torch.argsort(nodes, stable=True)
     sn, sv = nodes[order], vals[order]
     counts = torch.bincount(sn, minlength=n_n)
+    if vals.is_cuda:          # one thread per node adds its (stably sorted) contributions in order: fem_segment_sum_ordered
+        from ._lib import call
+        from .plan import _ptr, _stream
+        ptr = torch.zeros(n_n + 1, dtype=torch.int64, device=vals.device)
+        ptr[1:] = torch.cumsum(counts, 0)
+        sv = sv.contiguous()
+        out = torch.empty(n_n, dtype=torch.float64, device=vals.device)
+        with torch.cuda.device(vals.device):
+            call("fem_segment_sum_ordered", n_n, _ptr(ptr), _ptr(sv), _ptr(out), _stream())
+        return out
     starts = torch.cumsum(counts, 0) - counts
     rank = torch.arange(sn.numel(), device=sn.device) - starts[sn]
     out = torch.zeros(n_n, dtype=vals.dtype, device=vals.device)
@@ -58,3 +68,20 @@ def vector_traction(elements_s, coordinates, f_t_int, hatp_s, dhatp1_s, wf_s):
         v = (hatphi_s * (weight_s * f_t_int[c, -1]).reshape(1, -1)).t().reshape(-1)
         out.append(_scatter_ordered(v, nodes, n_n))
     return torch.stack(out)
+
+
+def vector_volume_plan(plan, f_v_int, hatp):
+    """f_V (2, n_n) on the device through the plan's node -> element incidence lists (fem_vector_volume): the same
+    ascending-integration-point order as ``vector_volume``, no sort, no atomics."""
+    import ctypes as C
+
+    import numpy as np
+
+    from ._lib import call
+    from .plan import _ptr, _stream
+    f = plan._f64(f_v_int, (2, plan.n_int))
+    h = np.ascontiguousarray(np.asarray(hatp, dtype=np.float64).reshape(plan.n_p, plan.n_q))
+    out = torch.empty((2, plan.n_n), dtype=torch.float64, device=plan.device)
+    with torch.cuda.device(plan.device):
+        call("fem_vector_volume", plan._h, _ptr(f), h.ctypes.data_as(C.POINTER(C.c_double)), _ptr(out), _stream())
+    return out

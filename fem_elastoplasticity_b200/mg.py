@@ -46,7 +46,7 @@ class Desc(C.Structure):
                 ("own_node_hi", C.c_int64), ("mask", C.c_void_p), ("dinv", C.c_void_p), ("xa", C.c_void_p), ("xb", C.c_void_p),
                 ("d", C.c_void_p), ("r", C.c_void_p), ("c1", C.c_double * MAX_DEGREE), ("c2", C.c_double * MAX_DEGREE),
                 ("ex_xa", Exchange), ("ex_xb", Exchange), ("ex_r", Exchange), ("lev", Level * MAX_LEVELS), ("coarse_inv", C.c_void_p),
-                ("err", C.c_void_p)]
+                ("K32", C.c_void_p), ("err", C.c_void_p)]
 
 
 def chebyshev_coefficients(lmax, ratio, degree):
@@ -129,7 +129,8 @@ class MultigridPCG:
     operators (Galerkin) from ``k_vals`` - for the Newton loop the elastic matrix, kept for every tangent solve: level 0
     always uses the matrix being solved.  ``solve`` mirrors TwoLevelPCG.solve."""
 
-    def __init__(self, plan, mask, part=None, free_mask=None, degree=3, ratio=8.0, max_coarse_dofs=2500, lattice=None, use_graph=True):
+    def __init__(self, plan, mask, part=None, free_mask=None, degree=2, ratio=8.0, max_coarse_dofs=2500, lattice=None, use_graph=True,
+                 smoother_f32=True):
         check_abi()
         self.plan, self.mask = plan, mask
         self.part = part if (part is not None and part.world > 1) else None
@@ -139,6 +140,8 @@ class MultigridPCG:
         if not 1 <= degree <= MAX_DEGREE:
             raise ValueError("degree")
         self.degree, self.ratio, self.use_graph = degree, ratio, use_graph
+        # FP32 copy of the matrix for the level-0 smoother / residual of the V-cycle (the CG itself stays on the FP64 matrix)
+        self.k32 = torch.zeros(plan.nnz, dtype=torch.float32, device=plan.device) if smoother_f32 else None
         self.device = dev = plan.device
         n = plan.n_dof
         z = lambda m, dt=torch.float64: torch.zeros(m, dtype=dt, device=dev)  # noqa: E731
@@ -172,26 +175,117 @@ class MultigridPCG:
         self.own_nodes = (own_rows[0] * LX, own_rows[1] * LX) if self.part is not None else (0, plan.n_n)
         self.layouts = level_layouts(LX, NY, owned, max_coarse_dofs=max_coarse_dofs)
         self.n_levels = len(self.layouts)
-        # ---- buffers
-        self.r, self.p, self.q, self.x, self.z, self.minv = (z(n) for _ in range(6))
+        # ---- buffers (on a partition the vectors whose ghost rows travel live in one symmetric-memory arena)
+        self._arena_slots, self._ex_ids = {}, {}
+        if self.part is not None:
+            self._make_arena(n)
+        a = self._vec
+        self.r, self.q, self.x, self.z, self.minv = (z(n) for _ in range(5))
+        self.p = a("p", n)
         self.scal = z(8)
-        self.v0 = {k: z(n) for k in ("xa", "xb", "d", "r")}
+        self.v0 = {"xa": a("xa0", n), "xb": a("xb0", n), "d": z(n), "r": a("r0", n)}
         self.lv = []
-        for lay in self.layouts:
+        for li, lay in enumerate(self.layouts):
             g0l, nrows, own_lo, own_hi, res_lo, res_hi = lay["ranks"][rank]
             nn = lay["nxn"] * nrows
             self.lv.append({"nxn": lay["nxn"], "nrows": nrows, "g0": g0l, "own": (own_lo, own_hi), "res": (res_lo, res_hi), "n": nn,
                             "N": lay["nrows_global"], "rep": lay["replicated"], "first_rep": lay["first_replicated"],
-                            "S": z(36 * nn), "dinv": z(2 * nn), **{k: z(2 * nn) for k in ("b", "xa", "xb", "d", "r")}, "lmax": None})
+                            "S": z(36 * nn), "dinv": z(2 * nn), "d": z(2 * nn), "b": a(f"b{li + 1}", 2 * nn),
+                            "xa": a(f"xa{li + 1}", 2 * nn), "xb": a(f"xb{li + 1}", 2 * nn), "r": a(f"r{li + 1}", 2 * nn), "lmax": None})
         self.coarse_inv, self.desc, self.setup_seconds, self.lmax0 = None, None, None, None
         self._graph, self._graph_key = None, None
         self.launches_last = 0
-        if self.part is not None:
-            self._init_exchanges()
 
     # -- multi-GPU plumbing (set-up collectives through torch.distributed; the solve uses fem_mg_exchange) ----------------
-    def _init_exchanges(self):
-        raise MultigridUnsupported("partitioned multigrid: exchanges not built yet")
+    def _vec(self, name, size):
+        """A zeroed vector; the arena slot ``name`` when this vector is exchanged between ranks."""
+        if name in self._arena_slots:
+            off, _ = self._arena_slots[name]
+            return self.arena[off:off + size]
+        return torch.zeros(size, dtype=torch.float64, device=self.device)
+
+    def _make_arena(self, n):
+        """One symmetric allocation (CUDA IPC mappings over NVLink) for every exchanged vector, the same offsets on every
+        rank, and the communication block: per exchange 16 flag words (one per source rank) + sequence number + ticket,
+        the sticky time-out word, and the lines of the scalar all-reduce."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        dev, world = self.device, self.world
+        nmax = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        slots = [("p", int(nmax.item())), ("xa0", int(nmax.item())), ("xb0", int(nmax.item())), ("r0", int(nmax.item()))]
+        for li, lay in enumerate(self.layouts):
+            if not lay["replicated"]:
+                sz = max(2 * lay["nxn"] * rk[1] for rk in lay["ranks"])
+                slots += [(f"xa{li + 1}", sz), (f"xb{li + 1}", sz), (f"r{li + 1}", sz)]
+            elif lay["first_replicated"]:
+                slots += [(f"b{li + 1}", 2 * lay["nxn"] * lay["nrows_global"])]
+        off = 0
+        for name, sz in slots:
+            self._arena_slots[name] = (off, sz)
+            self._ex_ids[name] = len(self._ex_ids)
+            off += sz + (sz & 1)
+        self.arena = symm.empty(off, dtype=torch.float64, device=dev)
+        self.arena.zero_()
+        self._arena_hdl = symm.rendezvous(self.arena, dist.group.WORLD)
+        self._arena_peers = [self.arena.data_ptr() if r == self.rank else self._arena_hdl.get_buffer(r, (off,), torch.float64).data_ptr() for r in range(world)]
+        n_ex = len(self._ex_ids)
+        self.W_SEQ = n_ex * MAX_PEERS
+        self.W_ERR = self.W_SEQ + 2 * n_ex
+        self.W_ARSEQ = self.W_ERR + 1
+        self.W_LINES = self.W_ARSEQ + 1
+        n_words = self.W_LINES + 512
+        self.comm = symm.empty(n_words, dtype=torch.int64, device=dev)
+        self.comm.zero_()
+        self._comm_hdl = symm.rendezvous(self.comm, dist.group.WORLD)
+        self._comm_views = [self.comm if r == self.rank else self._comm_hdl.get_buffer(r, (n_words,), torch.int64) for r in range(world)]
+        self._comm_peers = [v.data_ptr() for v in self._comm_views]
+        self._comm_table = (C.c_void_p * world)(*self._comm_peers)
+        torch.cuda.synchronize()
+        self._comm_hdl.barrier(channel=0)                # every arena and block is zeroed before any peer may store into it
+        torch.cuda.synchronize()
+
+    def _halo_desc(self, name, width, rank_rows):
+        """Exchange of the two boundary rows of vector ``name`` (rows of ``width`` nodes) with the neighbouring strips;
+        rank_rows[r] = (g0, nrows, own_lo, own_hi) of every rank."""
+        ex = Exchange()
+        if self.part is None or name not in self._ex_ids:
+            return ex
+        e, (off, _), rk = self._ex_ids[name], self._arena_slots[name], self.rank
+        g0, nrows, lo, hi = rank_rows[rk]
+        k = 0
+        for nb, src_row, exists in ((rk + 1, hi - 1, hi < nrows), (rk - 1, lo, lo > 0)):
+            if not exists:
+                continue
+            dst_row = g0 + src_row - rank_rows[nb][0]
+            assert 0 <= dst_row < rank_rows[nb][1] and not rank_rows[nb][2] <= dst_row < rank_rows[nb][3], (name, rk, nb, dst_row)
+            ex.src_off[k], ex.count[k] = src_row * width, width
+            ex.dst[k] = self._arena_peers[nb] + 8 * off + 16 * dst_row * width
+            ex.dst_flag[k] = self._comm_peers[nb] + 8 * (e * MAX_PEERS + rk)
+            ex.wait_flag[k] = self._comm_peers[rk] + 8 * (e * MAX_PEERS + nb)
+            k += 1
+        ex.n_send = ex.n_wait = k
+        ex.seq = self._comm_peers[rk] + 8 * (self.W_SEQ + 2 * e)
+        return ex
+
+    def _gather_desc(self, name, width, res):
+        """Every rank's share of the rows of ``name`` (first replicated level) to every other rank."""
+        ex = Exchange()
+        if self.part is None or name not in self._ex_ids:
+            return ex
+        e, (off, _), rk = self._ex_ids[name], self._arena_slots[name], self.rank
+        k = 0
+        for r in range(self.world):
+            if r == rk:
+                continue
+            ex.src_off[k], ex.count[k] = res[0] * width, (res[1] - res[0]) * width
+            ex.dst[k] = self._arena_peers[r] + 8 * off + 16 * res[0] * width
+            ex.dst_flag[k] = self._comm_peers[r] + 8 * (e * MAX_PEERS + rk)
+            ex.wait_flag[k] = self._comm_peers[rk] + 8 * (e * MAX_PEERS + r)
+            k += 1
+        ex.n_send = ex.n_wait = k
+        ex.seq = self._comm_peers[rk] + 8 * (self.W_SEQ + 2 * e)
+        return ex
 
     def _halo_rows(self, lv, t):
         """Forward halo of a level array viewed as (planes, nrows, width): ghost rows <- the neighbours' boundary rows."""
@@ -355,12 +449,26 @@ class MultigridPCG:
                 for k in range(self.degree):
                     L.c1[k], L.c2[k] = c1[k], c2[k]
         d.coarse_inv = self.coarse_inv.data_ptr()
+        d.K32 = self.k32.data_ptr() if self.k32 is not None else 0
         d.err = 0
         self._fill_exchanges(d)
         self.desc = d
 
     def _fill_exchanges(self, d):
-        pass
+        if self.part is None:
+            return
+        p, LX = self.part, self.lattice[4]
+        rows0 = [(r * p.ny_loc, p.ny_loc + 1 + (1 if r < self.world - 1 else 0), 1 if r > 0 else 0, p.ny_loc + 1) for r in range(self.world)]
+        d.ex_xa, d.ex_xb, d.ex_r = (self._halo_desc(k, LX, rows0) for k in ("xa0", "xb0", "r0"))
+        self.ex_p = self._halo_desc("p", LX, rows0)
+        for li, lay in enumerate(self.layouts):
+            L = d.lev[li]
+            if not lay["replicated"]:
+                rr = [rk[:4] for rk in lay["ranks"]]
+                L.ex_xa, L.ex_xb, L.ex_r = (self._halo_desc(f"{k}{li + 1}", lay["nxn"], rr) for k in ("xa", "xb", "r"))
+            elif lay["first_replicated"]:
+                L.ex_b = self._gather_desc(f"b{li + 1}", lay["nxn"], lay["ranks"][self.rank][4:6])
+        d.err = self._comm_peers[self.rank] + 8 * self.W_ERR
 
     # -- solve ----------------------------------------------------------------------------------------------------------
     def vcycle(self, k_vals, r, z, dot=None):
@@ -368,18 +476,38 @@ class MultigridPCG:
 
     def _exchange_p(self):
         if self.part is not None:
-            self.part.halo_exchange(self.p)
+            call("fem_mg_exchange_run", C.byref(self.ex_p), _ptr(self.p), C.c_void_p(self.desc.err), _stream())
+
+    def _update_p(self, it):
+        """p = z + beta p on the owned DOFs only: the ghost rows of p belong to the neighbours' pushes."""
+        lo, hi = 2 * self.own_nodes[0], 2 * self.own_nodes[1]
+        call("fem_mg_pcg_update_p", hi - lo, C.c_void_p(self.z.data_ptr() + 8 * lo), C.c_void_p(self.p.data_ptr() + 8 * lo), _ptr(self.scal), it, _stream())
+
+    def _sum_scal(self, lo, hi):
+        """scal[lo:hi] <- sum over the ranks, inside the stream (peer memory, no library call)."""
+        if self.part is not None:
+            call("fem_peer_allreduce", C.c_void_p(self.scal.data_ptr() + 8 * lo), hi - lo, _ptr(self.comm), self._comm_table, self.W_LINES,
+                 self.W_ARSEQ, self.W_ERR, self.rank, self.world, _stream())
+
+    def check_peer_error(self):
+        """The sticky time-out word of the in-kernel waits, MAX-reduced so that every rank raises together."""
+        if self.part is not None:
+            import torch.distributed as dist
+            err = self.comm[self.W_ERR:self.W_ERR + 1].clone()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            if int(err.item()) != 0:
+                raise RuntimeError("multigrid PCG: a peer did not publish within the time-out (tuning key peer_timeout_ms)")
 
     def _iteration(self, k_vals, it):
         n, s = self.plan.n_dof, self.scal
         self._exchange_p()
         call("fem_pcg_spmv_dot", self.plan._h, _ptr(k_vals), _ptr(self.p), _ptr(self.q), _ptr(self.mask), _ptr(s), it, _stream())
-        self._all_reduce(s[3:4])
+        self._sum_scal(3, 4)
         call("fem_mg_pcg_update_xr", n, _ptr(self.p), _ptr(self.q), _ptr(self.x), _ptr(self.r), _ptr(s), it, _stream())
         slot = 0 if it & 1 else 2
         self.vcycle(k_vals, self.r, self.z, s[slot:slot + 1])
-        self._all_reduce(s[1:3] if it % 2 == 0 else s[0:2])
-        call("fem_mg_pcg_update_p", n, _ptr(self.z), _ptr(self.p), _ptr(s), it, _stream())
+        self._sum_scal(*((1, 3) if it % 2 == 0 else (0, 2)))
+        self._update_p(it)
 
     def launches_per_iteration(self):
         k, L = self.degree, self.n_levels
@@ -391,18 +519,20 @@ class MultigridPCG:
             self.setup(k_vals)
         P, s, n = self.plan, self.scal, self.plan.n_dof
         P.jacobi(k_vals, self.mask, out=self.minv)
+        if self.k32 is not None:
+            call("fem_mg_to_f32", P.nnz, _ptr(k_vals), _ptr(self.k32), _stream())
         call("fem_mg_pcg_init", n, _ptr(rhs), _ptr(self.mask), _ptr(self.r), _ptr(self.x), _ptr(s), _stream())
-        self._all_reduce(s[0:5])
+        self._sum_scal(0, 5)
         self.vcycle(k_vals, self.r, self.z, s[0:1])
-        self._all_reduce(s[0:1])
-        call("fem_mg_pcg_update_p", n, _ptr(self.z), _ptr(self.p), _ptr(s), -1, _stream())
+        self._sum_scal(0, 1)
+        self._update_p(-1)
         n_it = iters if iters is not None else maxit
         it, rel = 0, float("inf")
         h = s.cpu()
         bb = float(h[4])
         if iters is None and (bb == 0.0 or float(h[1]) <= rtol * rtol * bb):
             return self.x, 0, 0.0 if bb == 0.0 else (float(h[1]) / bb) ** 0.5
-        graph = self._pair_graph(k_vals) if (self.use_graph and self.part is None and n_it >= 4) else None
+        graph = self._pair_graph(k_vals) if (self.use_graph and n_it >= 4) else None
         self.launches_last = 0
         while it < n_it:
             nxt = n_it if iters is not None else min(n_it, (it // check_every + 1) * check_every)
@@ -414,6 +544,7 @@ class MultigridPCG:
                     self._iteration(k_vals, it)
                     it += 1
             h = s.cpu()
+            self.check_peer_error()
             if not torch.isfinite(h[1]):
                 raise ArithmeticError("multigrid PCG breakdown: residual is not finite")
             rel = float((h[1] / h[4]).sqrt()) if h[4] > 0 else 0.0

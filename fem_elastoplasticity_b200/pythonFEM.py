@@ -128,12 +128,13 @@ def get_elastic_stiffness_matrix(elements, coordinates, shear, bulk, dhatp1, dha
     plan = FemPlan(np.asarray(elements).astype(np.int64), coordinates, dhatp1, dhatp2, wf, device=device)
     k_vals = plan.assemble_elastic(shear, bulk)
     weight = plan.weight.cpu().numpy().reshape(1, -1).copy()
+    if not host_matrices:                               # large meshes: values stay on the device (DeviceMatrix), no host B / D
+        K = DeviceMatrix(plan, k_vals)
+        return (K, weight) if variant == "elasticity2d" else (K, plan, weight, None, None, None)
     K = _host_K(plan, k_vals)
     if variant == "elasticity2d":
         return K, weight
     i_d, j_d = _d_indices(plan.n_int)
-    if not host_matrices:
-        return K, plan, weight, i_d, j_d, None
     B = _host_B(plan, elements)
     B._fem_plan = plan
     vd = plan.elastic_dmat(shear, bulk).cpu().numpy()
@@ -187,18 +188,19 @@ def strain(plan_or_B, U):
     return plan.strain(u).cpu().numpy()
 
 
-def assemble_tangent(plan_or_K, ds, mode="reference", D_elast=None, K_elast=None):
+def assemble_tangent(plan_or_K, ds, mode="reference", D_elast=None, K_elast=None, host_matrix=True):
     """K_tangent (:1047-1050).  ``mode='reference'`` evaluates K_elast + B^T (D_p - D_elast) B in the reference's own
     order (bit-identical; needs ``K_elast`` from get_elastic_stiffness_matrix and its ``D``); ``mode='direct'`` sums
     B^T (w ds) B in one pass (fastest, equal within rounding)."""
     plan = _plan_of(plan_or_K)
+    wrap = _host_K if host_matrix else DeviceMatrix     # host_matrix=False: values stay on the device (DeviceMatrix)
     if mode == "direct":
-        return _host_K(plan, plan.assemble_tangent(ds))
+        return wrap(plan, plan.assemble_tangent(ds))
     K_elast = plan_or_K if K_elast is None else K_elast
     if D_elast is None or not hasattr(D_elast, "_fem_shear") or not hasattr(K_elast, "_fem_vals"):
         raise TypeError("mode='reference' needs K_elast and D returned by get_elastic_stiffness_matrix")
     vals = plan.assemble_tangent_ref(ds, D_elast._fem_shear, D_elast._fem_bulk, K_elast._fem_vals)
-    return _host_K(plan, vals)
+    return wrap(plan, vals)
 
 
 def internal_force(plan_or_B, s):
@@ -207,11 +209,49 @@ def internal_force(plan_or_B, s):
     return plan.internal_force(np.asarray(s, dtype=np.float64)[0:3]).cpu().numpy().reshape(-1, 1)
 
 
-def solve_increment(K_tangent, F, Q, rtol=1e-13, maxit=200000):
-    """dU with dU[Q] = K_tangent[Q,Q]^-1 (-F[Q]) (:1062-1066), by Jacobi-PCG on the device; returns (2, n_n)."""
+class DeviceMatrix:
+    """What ``assemble_tangent(..., host_matrix=False)`` returns: the values stay in HBM next to the plan's pattern, and the
+    SciPy ``csc_matrix`` the reference would hold (pruned of exact zeros) is only built when ``.tocsc()`` / ``.host`` is
+    asked for.  ``solve_increment`` and ``stopping_criterion`` accept it wherever they accept a matrix."""
+
+    def __init__(self, plan, k_vals):
+        self._fem_plan, self._fem_vals, self._host = plan, k_vals, None
+        self.shape = (plan.n_dof, plan.n_dof)
+
+    @property
+    def host(self):
+        if self._host is None:
+            self._host = _host_K(self._fem_plan, self._fem_vals)
+        return self._host
+
+    def tocsc(self):
+        return self.host
+
+    def tocsr(self):
+        return self.host.tocsr()
+
+
+def solve_increment(K_tangent, F, Q, rtol=1e-13, maxit=200000, precond="auto", K_elast=None):
+    """dU with dU[Q] = K_tangent[Q,Q]^-1 (-F[Q]) (:1062-1066), by preconditioned CG on the device; returns (2, n_n).
+    ``precond``: "multigrid" (geometric V-cycle, mg.py: uniform-lattice meshes), "jacobi", or "auto" = multigrid where the
+    mesh allows it.  The multigrid hierarchy is built once per (mesh, Q) from ``K_elast`` (default: the first matrix seen)."""
     plan = _plan_of(K_tangent)
     mask = plan.mask_u8(Q)
     rhs = -np.asarray(F, dtype=np.float64).reshape(-1)
+    if precond in ("auto", "multigrid"):
+        from .mg import MultigridPCG, MultigridUnsupported
+        cache = plan.__dict__.setdefault("_mg_cache", {})
+        key = hash(mask.cpu().numpy().tobytes())
+        if key not in cache:
+            try:
+                cache[key] = MultigridPCG(plan, mask).setup((K_elast if K_elast is not None else K_tangent)._fem_vals)
+            except MultigridUnsupported:
+                if precond == "multigrid":
+                    raise
+                cache[key] = None
+        if cache[key] is not None:
+            x, its, rel = cache[key].solve(K_tangent._fem_vals, plan._f64(rhs), rtol=rtol, maxit=min(maxit, 2000))
+            return x.cpu().numpy().reshape((2, -1), order='F')
     x, its, rel = plan.pcg(K_tangent._fem_vals, rhs, mask, rtol=rtol, maxit=maxit)
     dU = x.cpu().numpy().reshape((2, -1), order='F')
     return dU

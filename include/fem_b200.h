@@ -248,6 +248,8 @@ typedef struct fem_mg_desc {
   fem_mg_exchange ex_xa, ex_xb, ex_r;
   fem_mg_level lev[FEM_MG_MAX_LEVELS]; /* lev[l-1] = level l */
   const double* coarse_inv;          /* dense inverse of the last level, [n_c][n_c], n_c = 2*nxn*nrows of that level */
+  const float* K32;                  /* optional FP32 copy of K_vals (fem_mg_to_f32): streamed by the level-0 smoother and residual
+                                        instead of the FP64 values (half the bytes; sums stay FP64); NULL = use K_vals */
   uint64_t* err;                     /* sticky word: a wait timed out (NULL on one GPU) */
 } fem_mg_desc;
 int fem_mg_sizeof(int which); /* sizeof fem_mg_exchange (0), fem_mg_level (1), fem_mg_desc (2): checked by the binding */
@@ -266,6 +268,13 @@ int fem_mg_stencil_to_dense(int nxn, int nrows, const double* S, double* A, fem_
  * over this rank's unknowns.  r must be zero on masked DOFs.                                         */
 int fem_mg_vcycle(const fem_plan* plan, const fem_mg_desc* desc, const double* K_vals, const double* r, double* z, double* dot,
                   fem_stream stream);
+/* vals[0:n] (n <= 8, device) <- sum over all ranks, through peer memory (no library call, CUDA-graph capturable).
+ * comm: this rank's communication block; peers[r]: rank r's block as mapped here; lines_word: first of FEM_PEER_ALLREDUCE_WORDS
+ * 8-byte words reserved for the lines; seq_word: sequence counter; err_word: sticky time-out word (all zero-filled once).   */
+#define FEM_PEER_ALLREDUCE_WORDS 512
+int fem_peer_allreduce(double* vals, int n, void* comm, const void* const* peers, int64_t lines_word, int64_t seq_word, int64_t err_word,
+                       int rank, int world, fem_stream stream);
+int fem_mg_to_f32(int64_t n, const double* src, float* dst, fem_stream stream); /* n % 4 == 0 (nnz of the 2x2-block pattern) */
 int fem_mg_exchange_run(const fem_mg_exchange* ex, double* v, uint64_t* err, fem_stream stream);
 /* CG steps around the V-cycle (scal as in fem_pcg_*: [0]/[2] r'z by iteration parity, [1] r'r, [3] p'Kp, [4] |b|^2):
  * init: r = mask .* rhs, x = 0, scal zeroed, [1] = [4] = |r|^2;  update_xr: x += alpha p, r -= alpha q, [1] += r'r;
@@ -285,8 +294,17 @@ int fem_vec_axpby(int64_t n, double a, const double* x, double b, const double* 
  * points of the elements around node n (Plasticity2D_DP/pythonFEM.py:760-816)                      */
 int fem_transform(const fem_plan* plan, const double* q_int, double* q_node, fem_stream stream);
 
+/* Load vectors of the linear-elastic demo (Elasticity2D/pythonFEM.py:246-364).
+ * fem_vector_volume: out[c*n_n + n] = sum_g hatp[la, q] * (weight[g] * f_int[c*n_int + g]) over the integration points of the
+ *   elements around node n in ascending g - SciPy's summation order of the reference's COO triplets (:281-290), bit-identical.
+ *   h_hatp: HOST (n_p, n_q) row-major basis values (get_local_basis_volume).  out is (2, n_n) like the reference's f_V.
+ * fem_segment_sum_ordered: out[s] = sequential sum of vals[seg_ptr[s] : seg_ptr[s+1]] (one thread per segment): the ordered
+ *   duplicate summation for contributions stably sorted by node (surface tractions, :327-362).                          */
+int fem_vector_volume(const fem_plan* plan, const double* f_int, const double* h_hatp, double* out, fem_stream stream);
+int fem_segment_sum_ordered(int64_t n_seg, const int64_t* seg_ptr, const double* vals, double* out, fem_stream stream);
+
 /* launch-shape knobs for benchmarking ("return_map_variant", "assemble_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm",
- * "spmv_staged", "peer_timeout_ms");
+ * "spmv_staged", "peer_timeout_ms", "strain_variant");
  * value 0 restores the default.  Results never depend on them.                                     */
 int fem_set_tuning(const char* key, int value);
 

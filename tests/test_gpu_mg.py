@@ -54,7 +54,7 @@ def test_hierarchy_and_vcycle_match_numpy_statement(fem, nx, ny):
     r = dp_return_map(fem["meshgen"].synthetic_strain(P.n_int), None, G, Kb, eta, c)
     k_tan = P.assemble_tangent(r["ds"])
     mask = P.mask_u8(m["Q"])
-    M = mg.MultigridPCG(P, mask, degree=3, ratio=8.0, max_coarse_dofs=120).setup(k_el)
+    M = mg.MultigridPCG(P, mask, degree=3, ratio=8.0, max_coarse_dofs=120, smoother_f32=False).setup(k_el)
     assert M.n_levels >= 3
     q = mask.cpu().numpy().astype(bool)
     Kel, Ktan = P.to_scipy_csr(k_el), P.to_scipy_csr(k_tan)
@@ -117,6 +117,10 @@ def test_multigrid_pcg_solves_the_newton_system(fem):
         M.use_graph = False
         x2, n2, _ = M.solve(k_tan, -F, rtol=1e-10)
         assert n2 == n_it and float((x2 - x).abs().max()) <= 1e-9 * float(x.abs().max())
+        # the default streams an FP32 copy of the matrix in the smoother: same solution, (almost) the same count as FP64
+        M64 = mg.MultigridPCG(P, mask, smoother_f32=False).setup(k_el)
+        x3, n3, _ = M64.solve(k_tan, -F, rtol=1e-10)
+        assert abs(n3 - n_it) <= 2 and float((x3 - x).abs().max()) <= 1e-8 * float(x.abs().max()), (n3, n_it)
     print("multigrid PCG iterations:", its)
     assert max(its.values()) <= 60 and its[384] <= its[96] + 8
 
