@@ -420,6 +420,13 @@ def run_gpu(args):
         assert true_rel <= 10 * args.rtol, f"multigrid solve: true residual {true_rel:.2e}"
     # fixed number of Jacobi-PCG iterations on the same system: the per-iteration roofline figure of K7-K9
     t_jac = iso(lambda: pcg.solve(k_tan, rhs, iters=args.pcg_iters), reps=3)
+    t_mg_cheb = t_mg_resid = t_spmv = 0.0
+    if mgs is not None:                                  # the level-0 kernels of the V-cycle and the CG's SpMV, on their own
+        xa, xb = mgs.v0["xa"], mgs.v0["xb"]
+        xa.copy_(mgs.x)
+        t_mg_cheb = iso(lambda: mgs.fine_step(k_tan, rhs, xa, xb, mode=2, step=1), reps=10)
+        t_mg_resid = iso(lambda: mgs.fine_step(k_tan, rhs, xa, mgs.v0["r"], mode=1), reps=10)
+        t_spmv = iso(lambda: P.spmv(k_tan, mgs.x, mask=mask, out=mgs.q), reps=10)
     t_tan_only = iso(lambda: P.assemble_tangent(rm["ds"], out=k_tan))
     t_el_only = iso(lambda: P.assemble_elastic(G, Kb, out=k_el))
     # ---- correctness carried by the run itself (N > 1): see multi_gpu_checks
@@ -510,10 +517,10 @@ def run_gpu(args):
         del Kel_h, cp
     # ---- reduce over ranks (max time)
     vec = torch.tensor([total_ms, per["strain"], per["return_map"], per["assembly"], per["pcg"], per["criterion"], e2e_ms,
-                        t_tan_only, t_el_only, t_jac], dtype=torch.float64, device=dev)
+                        t_tan_only, t_el_only, t_jac, t_mg_cheb, t_mg_resid, t_spmv], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-    total_ms, t_strain, t_rm, t_asm, t_pcg, t_crit, e2e_ms, t_tan_only, t_el_only, t_jac = [float(v) for v in vec.cpu()]
+    total_ms, t_strain, t_rm, t_asm, t_pcg, t_crit, e2e_ms, t_tan_only, t_el_only, t_jac, t_mg_cheb, t_mg_resid, t_spmv = [float(v) for v in vec.cpu()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -531,6 +538,13 @@ def run_gpu(args):
         "strain": 12.0 * P.n_e + 8.0 * P.n_dof + 24.0 * P.n_int,
         "pcg_iter": 12.0 * nnz_rank + 148.0 * n_dof_rank,
         "spmv": 12.0 * nnz_rank + 4.0 * (n_dof_rank + 1) + 16.0 * n_dof_rank,
+        # bytes THIS implementation has to move (block pattern: 8 B/nnz of values + one 16-bit block position per 4 values,
+        # node pointers, x once, y once, mask; Jacobi-PCG vector kernels: 10 vector passes) - ncu agrees within 4 % (profiles/r2c)
+        "spmv_own": 8.5 * nnz_rank + (4.0 + 16.0 + 16.0 + 2.0) * P.n_n,
+        "pcg_iter_own": 8.5 * nnz_rank + 38.0 * P.n_n + 80.0 * n_dof_rank,
+        # level-0 multigrid step: FP32 values (4 B/nnz) + block positions + node pointers + b, D^-1, d, x in, d, x out
+        "mg_cheb": (4.5 if (mgs is not None and mgs.k32 is not None) else 8.5) * nnz_rank + 4.0 * P.n_n + 48.0 * n_dof_rank,
+        "mg_resid": (4.5 if (mgs is not None and mgs.k32 is not None) else 8.5) * nnz_rank + 6.0 * P.n_n + 24.0 * n_dof_rank,
     }
     pcg_ms_iter = t_jac / max(args.pcg_iters, 1)
     conv = None
@@ -545,22 +559,43 @@ def run_gpu(args):
                 "cuda_graph": bool(mgs._graph is not None),
                 "history": "point-Jacobi 57 500 iterations / 41.7 s, two-level 1 900 iterations / 1.77 s on the same 16M-element system (round 1 / profiles/r2j)",
                 "two_level": tl_conv}
-    traffic = None
+    ncu_traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("assemble_rows_kernel")
+            ncu_traffic = json.load(f)
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": "assemble_rows_tmap_kernel<TANGENT,FORCE> (K_tangent + internal force, one pass, TMA-staged)",
-            "achieved": gbs(algo["assembly"], t_asm), "peak": peak, "unit": "GB/s", "frac": gbs(algo["assembly"], t_asm) / peak,
-            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["assembly"],
-            "frac_of_8TBs_nominal": gbs(algo["assembly"], t_asm) / 8000.0}
+    asm_roof = {"kernel": "assemble_rows_tmap_kernel<TANGENT,FORCE> (K_tangent + internal force, one pass, TMA-staged)",
+                "achieved": gbs(algo["assembly"], t_asm), "frac": gbs(algo["assembly"], t_asm) / peak, "ms": t_asm,
+                "algorithmic_bytes": algo["assembly"], "traffic": ncu_traffic.get("assemble_rows_kernel"),
+                "share_of_step": t_asm / ms_step}
+    if mgs is not None:
+        # the dominant kernel of the converged step: the level-0 Chebyshev step of the V-cycle (2*degree - 1 launches per CG
+        # iteration), the smoother's vector updates fused into the epilogue of the block-CSR SpMV
+        n_cheb = (2 * mgs.degree - 1) * int(solve_info["iterations"]) + 2 * mgs.degree - 1
+        roof = {"bound": "hbm", "kernel": "mg_fine_tiles_kernel<CHEB> (level-0 Chebyshev smoothing step of the multigrid V-cycle: block-CSR SpMV on the "
+                                          f"{'FP32' if mgs.k32 is not None else 'FP64'} matrix copy + fused vector updates)",
+                "achieved": gbs(algo["mg_cheb"], t_mg_cheb), "peak": peak, "unit": "GB/s", "frac": gbs(algo["mg_cheb"], t_mg_cheb) / peak,
+                "traffic": ncu_traffic.get("mg_fine_tiles_kernel_cheb"), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["mg_cheb"],
+                "ms_per_launch": t_mg_cheb, "launches_per_step": n_cheb, "share_of_step": n_cheb * t_mg_cheb / ms_step,
+                "frac_of_8TBs_nominal": gbs(algo["mg_cheb"], t_mg_cheb) / 8000.0,
+                "assembly": asm_roof}
+    else:
+        roof = {"bound": "hbm", "kernel": asm_roof["kernel"], "achieved": asm_roof["achieved"], "peak": peak, "unit": "GB/s", "frac": asm_roof["frac"],
+                "traffic": asm_roof["traffic"], "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["assembly"],
+                "frac_of_8TBs_nominal": asm_roof["achieved"] / 8000.0}
     rooflines = {k: {"achieved": gbs(algo[a], ms), "frac": gbs(algo[a], ms) / peak, "ms": ms, "algorithmic_bytes": algo[a]}
                  for k, a, ms in (("dp_return_map", "return_map", t_rm), ("strain", "strain", t_strain),
+                                  ("assemble_tangent_force(in step)", "assembly", t_asm),
                                   ("assemble_tangent_only(isolated)", "tangent_only", t_tan_only),
                                   ("assemble_elastic(isolated)", "elastic", t_el_only),
                                   ("pcg_iteration(spmv+2 vector kernels)", "pcg_iter", pcg_ms_iter),
-                                  ("criterion(3 spmv)", "spmv", t_crit / 3.0))}
+                                  ("pcg_iteration, bytes of this implementation", "pcg_iter_own", pcg_ms_iter),
+                                  ("criterion(3 spmv)", "spmv", t_crit / 3.0)) if ms > 0}
+    if mgs is not None:
+        rooflines.update({k: {"achieved": gbs(algo[a], ms), "frac": gbs(algo[a], ms) / peak, "ms": ms, "algorithmic_bytes": algo[a]}
+                          for k, a, ms in (("mg_fine_step_cheb(isolated)", "mg_cheb", t_mg_cheb), ("mg_fine_step_residual(isolated)", "mg_resid", t_mg_resid),
+                                           ("spmv(isolated), CSR bytes", "spmv", t_spmv), ("spmv(isolated), bytes of this implementation", "spmv_own", t_spmv))})
     line = {
         "metric": METRIC, "value": n_e_tot / (t_asm * 1e-3) / 1e6, "unit": "Melem/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,

@@ -72,6 +72,7 @@ SIGNATURES = {
     "fem_mg_stencil_to_dense": [_i32, _i32, _vp, _vp, _vp],
     "fem_mg_vcycle": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "fem_peer_allreduce": [_vp, _i32, _vp, C.POINTER(_vp), _i64, _i64, _i64, _i32, _i32, _vp],
+    "fem_mg_fine_step": [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp],
     "fem_mg_to_f32": [_i64, _vp, _vp, _vp],
     "fem_mg_exchange_run": [_vp, _vp, _vp, _vp],
     "fem_mg_pcg_init": [_i64, _vp, _vp, _vp, _vp, _vp, _vp],

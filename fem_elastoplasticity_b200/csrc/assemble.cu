@@ -484,6 +484,9 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A,
     }
 }
 
+#ifndef FEM_ASM_UNROLL
+#define FEM_ASM_UNROLL 2  // incidence steps per rotation of the register queue in variant D (1, 2, 4 or 8)
+#endif
 // ---- variant D: persistent, software-pipelined TMA staging ------------------------------------------------------
 // Same staging and arithmetic as variant C, but each warp walks many slices and keeps the TMA engine one half-slice
 // ahead: box 0 of slice s+1 is requested as soon as the incidences living in box 0 of slice s are consumed, box 1 of
@@ -607,12 +610,17 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
         else if (nb == 2) { mbar_wait(bar1, ph1); ph1 ^= 1; }
       }
       if (pass == 0 || (staged && nb == 2)) {
+        // The incidence words live in registers; a runtime loop can only address them by rotating the queue (16 register
+        // moves per step in SASS: 20 % of the kernel's instructions, all on the serial path - profiles/r2c_D).  UN steps
+        // are unrolled with static indices and the queue is rotated by UN at once: back in place after CH steps.
+        constexpr int UN = FEM_ASM_UNROLL;
+        static_assert(CH % UN == 0, "unroll factor");
 #pragma unroll 1
-        for (int i = 0; i < CH; ++i) {  // rotate the whole queue so that it is back in place for the next pass
-          const uint32_t word = words[0];
+        for (int i0 = 0; i0 < CH; i0 += UN) {
 #pragma unroll
-          for (int k = 0; k + 1 < CH; ++k) words[k] = words[k + 1];
-          words[CH - 1] = word;
+        for (int k0 = 0; k0 < UN; ++k0) {
+          const int i = i0 + k0;
+          const uint32_t word = words[k0];
           if (!(word & 0x80000000u)) continue;
           const int li = word & 0x1FF;
           if (staged && ((li >= bw) != (pass == 1))) continue;
@@ -673,6 +681,16 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
             }
 #undef FEM_UPD
           }
+        }
+        if (UN < CH) {  // rotate by UN
+          uint32_t head[UN];
+#pragma unroll
+          for (int k = 0; k < UN; ++k) head[k] = words[k];
+#pragma unroll
+          for (int k = 0; k + UN < CH; ++k) words[k] = words[k + UN];
+#pragma unroll
+          for (int k = 0; k < UN; ++k) words[CH - UN + k] = head[k];
+        }
         }
       }
       __syncwarp();  // every lane is done reading this pass's box: it may be overwritten by the next slice's copy

@@ -240,9 +240,32 @@ struct MgFineEpilogue {
   double c1, c2;
   bool want_dot;
   int64_t own_lo, own_hi;  // ghost nodes are never written: their owners store them (fem_mg_exchange)
-  __device__ __forceinline__ void operator()(const int64_t a, const double acc0, const double acc1, double& dot) const {
-    if (a < own_lo || a >= own_hi) return;
-    const double2 bi = b[a];
+  int group;               // lanes per node (>= 4)
+  // operands of the update, one per lane of the node's group, requested together with the matrix values
+  __device__ __forceinline__ double2 prefetch(const int64_t a, const int sub) const {
+    if (a >= own_lo && a < own_hi) {
+      if (sub == 0) return b[a];
+      if (MODE != MG_RESID) {
+        if (sub == 1) return dinv[a];
+        if (sub == 2 && c1 != 0.0) return d[a];
+        if (sub == 3) return x[a];
+      }
+    }
+    return make_double2(0.0, 0.0);
+  }
+  __device__ __forceinline__ void operator()(const int64_t a, const bool lead, const double acc0, const double acc1, double& dot, const double2 pf) const {
+    const int base = (threadIdx.x & 31) & ~(group - 1);
+    double2 di = make_double2(0.0, 0.0), dd = di, xi = di;
+    if (MODE != MG_RESID) {  // executed by every lane of the warp: the lead lane collects its neighbours' operands
+      di.x = __shfl_sync(0xffffffffu, pf.x, base + 1);
+      di.y = __shfl_sync(0xffffffffu, pf.y, base + 1);
+      dd.x = __shfl_sync(0xffffffffu, pf.x, base + 2);
+      dd.y = __shfl_sync(0xffffffffu, pf.y, base + 2);
+      xi.x = __shfl_sync(0xffffffffu, pf.x, base + 3);
+      xi.y = __shfl_sync(0xffffffffu, pf.y, base + 3);
+    }
+    if (!lead || a < own_lo || a >= own_hi) return;
+    const double2 bi = pf;
     double r0 = bi.x - acc0, r1 = bi.y - acc1;
     if (MODE == MG_RESID) {
       if (mask) {
@@ -253,15 +276,11 @@ struct MgFineEpilogue {
       out[a] = make_double2(r0, r1);
       return;
     }
-    const double2 di = dinv[a];  // zero on masked DOFs: d and x stay zero there
+    // dinv is zero on masked DOFs: d and x stay zero there
     double2 dn = make_double2(c2 * di.x * r0, c2 * di.y * r1);
-    if (c1 != 0.0) {
-      const double2 dd = d[a];
-      dn.x = fma(c1, dd.x, dn.x);
-      dn.y = fma(c1, dd.y, dn.y);
-    }
+    dn.x = fma(c1, dd.x, dn.x);  // dd == 0 when c1 == 0 (first step of a sweep)
+    dn.y = fma(c1, dd.y, dn.y);
     d[a] = dn;
-    const double2 xi = x[a];
     const double2 xo = make_double2(xi.x + dn.x, xi.y + dn.y);
     out[a] = xo;
     if (want_dot) dot = fma(bi.x, xo.x, fma(bi.y, xo.y, dot));
@@ -269,7 +288,7 @@ struct MgFineEpilogue {
 };
 
 template <int GROUP, int MODE, class VT>
-__global__ void __launch_bounds__(FEM_SPMV_THREADS) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                                          const int32_t* __restrict__ tile_seg, const VT* __restrict__ vals,
                                                                          const double* x, const MgFineEpilogue<MODE> epi, double* dot_out) {
@@ -540,8 +559,9 @@ int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const d
                    double* dot, cudaStream_t st) {
   MgFineEpilogue<MODE> epi{reinterpret_cast<const double2*>(b), reinterpret_cast<const double2*>(D->dinv), reinterpret_cast<double2*>(D->d),
                            reinterpret_cast<const double2*>(x), reinterpret_cast<double2*>(out), D->mask, c1, c2, dot != nullptr,
-                           D->own_node_lo, D->own_node_hi};
+                           D->own_node_lo, D->own_node_hi, 0};
   const SpmvShape sh = spmv_shape(P);
+  epi.group = sh.group;
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
 #define MGT(G) mg_fine_tiles_kernel<G, MODE, VT><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot)
@@ -778,6 +798,16 @@ extern "C" int fem_mg_vcycle(const fem_plan* P, const fem_mg_desc* D, const doub
     swap();
   }
   return FEM_OK;
+}
+
+// One level-0 step on its own (benchmarks, tests): mode 1: out = mask .* (b - K x); mode 2: d = c1 d + c2 D^-1 (b - K x),
+// out = x + d, *dot += b'out if dot != NULL.  K_vals is used unless the descriptor carries an FP32 copy.
+extern "C" int fem_mg_fine_step(const fem_plan* P, const fem_mg_desc* D, int mode, const double* K_vals, const double* b, const double* x,
+                                double* out, double c1, double c2, double* dot, fem_stream stream) {
+  FEM_REQUIRE(P && D && K_vals && b && x && out && (mode == MG_RESID || mode == MG_CHEB) && out != x, "arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == MG_RESID) return launch_fine<MG_RESID>(P, D, K_vals, b, x, out, 0.0, 0.0, nullptr, st);
+  return launch_fine<MG_CHEB>(P, D, K_vals, b, x, out, c1, c2, dot, st);
 }
 
 extern "C" int fem_mg_pcg_init(int64_t n, const double* rhs, const uint8_t* mask, double* r, double* x, double* scal, fem_stream stream) {

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
 
 // x staged through shared memory by bulk async copies (spmv.cuh: spmv_tiles)
 template <int GROUP>
-__global__ void __launch_bounds__(FEM_SPMV_THREADS) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                          const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                          const double* __restrict__ x, double* __restrict__ y,

@@ -228,6 +228,10 @@ class DistributedPCG:
         # fastest: 0.122 vs 0.212 ms/iteration at 8 GPUs x 2M DOFs); "auto": fused, NCCL if symmetric memory is unavailable
         self.peer = None
         self.fused = False
+        if not hasattr(part, "row_dofs"):                 # general (RCB) partition: index-list halos, NCCL exchanges
+            if peer in (True, "fused"):
+                raise ValueError("the peer-memory exchanges are built for the strip partition")
+            peer = False
         if ops is None and part.world > 1 and peer in ("auto", True, "fused"):
             try:
                 self.peer = PeerHalo(part, self.ops.n, self.r.device)

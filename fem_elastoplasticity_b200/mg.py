@@ -474,6 +474,12 @@ class MultigridPCG:
     def vcycle(self, k_vals, r, z, dot=None):
         call("fem_mg_vcycle", self.plan._h, C.byref(self.desc), _ptr(k_vals), _ptr(r), _ptr(z), _ptr(dot), _stream())
 
+    def fine_step(self, k_vals, b, x, out, mode=2, step=1, dot=None):
+        """One level-0 step of the V-cycle on its own: mode 2 = Chebyshev step ``step`` of the smoother, 1 = residual."""
+        c1 = self.desc.c1[step] if mode == 2 else 0.0
+        c2 = self.desc.c2[step] if mode == 2 else 0.0
+        call("fem_mg_fine_step", self.plan._h, C.byref(self.desc), mode, _ptr(k_vals), _ptr(b), _ptr(x), _ptr(out), c1, c2, _ptr(dot), _stream())
+
     def _exchange_p(self):
         if self.part is not None:
             call("fem_mg_exchange_run", C.byref(self.ex_p), _ptr(self.p), C.c_void_p(self.desc.err), _stream())

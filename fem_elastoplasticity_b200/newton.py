@@ -187,9 +187,17 @@ def footing_driver(mesh, plan=None, level=None, max_steps=1000, pcg_rtol=1e-13, 
             "Ep": ep_old.cpu().numpy()}
 
 
-def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi", coarse_cells=8, refine=0):
-    """tsx-tunnel load stepping (tsx-tunnel/pythonFEM.py:1661-1830) for P1 on the device."""
+def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct", log=None, precond="jacobi", coarse_cells=8, refine=0,
+               part=None):
+    """tsx-tunnel load stepping (tsx-tunnel/pythonFEM.py:1661-1830) for P1 on the device.  ``part``: a
+    partition.GeneralPartition of the (global) mesh when run one process per GPU; the returned U is then the local array
+    (owned nodes first, ghosts after)."""
     from . import pythonFEM as api
+    if part is not None and part.world > 1:
+        lm = part.local_mesh({"coordinates": coords, "elements": elem}, "cpu")
+        coords, elem = lm["coordinates"].numpy(), lm["elements"].numpy()
+    else:
+        part = None
     et = api.LagrangeElementType.P1
     xi, wf = api.get_quadrature_volume(et)
     _, d1, d2 = api.get_local_basis_volume(et, xi)
@@ -212,7 +220,7 @@ def tsx_driver(coords, elem, max_steps=100, pcg_rtol=1e-13, tangent_mode="direct
     n_int = P.n_int
     ones = np.ones(n_int)
     ns = NewtonSolver(P, shear0 * ones, bulk0 * ones, eta0 * ones, c0 * ones, q, pcg_rtol=pcg_rtol, tangent_mode=tangent_mode,
-                      precond=precond, coarse_cells=coarse_cells, refine=refine)
+                      precond=precond, coarse_cells=coarse_cells, refine=refine, part=part)
     s_init = torch.as_tensor(np.tile(s0.reshape(-1, 1), (1, n_int))).to(P.device)
     f0 = P.internal_force(s_init)                                     # :1737
     rhs = axpby(-1.0, f0, 0.0, f0)

@@ -274,6 +274,10 @@ int fem_mg_vcycle(const fem_plan* plan, const fem_mg_desc* desc, const double* K
 #define FEM_PEER_ALLREDUCE_WORDS 512
 int fem_peer_allreduce(double* vals, int n, void* comm, const void* const* peers, int64_t lines_word, int64_t seq_word, int64_t err_word,
                        int rank, int world, fem_stream stream);
+/* one level-0 step of the V-cycle on its own (benchmarks / tests): mode 1: out = mask .* (b - K x); mode 2 (Chebyshev step):
+ * d = c1 d + c2 D^-1 (b - K x), out = x + d, *dot += b'out (dot nullable); d, D^-1, mask and the optional FP32 matrix from desc */
+int fem_mg_fine_step(const fem_plan* plan, const fem_mg_desc* desc, int mode, const double* K_vals, const double* b, const double* x,
+                     double* out, double c1, double c2, double* dot, fem_stream stream);
 int fem_mg_to_f32(int64_t n, const double* src, float* dst, fem_stream stream); /* n % 4 == 0 (nnz of the 2x2-block pattern) */
 int fem_mg_exchange_run(const fem_mg_exchange* ex, double* v, uint64_t* err, fem_stream stream);
 /* CG steps around the V-cycle (scal as in fem_pcg_*: [0]/[2] r'z by iteration parity, [1] r'r, [3] p'Kp, [4] |b|^2):

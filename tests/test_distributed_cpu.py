@@ -280,3 +280,89 @@ def DistributedPCGJacobiCount(K, free, rhs):
     part = StripPartition(10, n_rows // 11 - 1, 0, 1)
     pcg = DistributedPCG(None, part, free, ops=NumpyOps(K))
     return pcg.solve(None, rhs, rtol=1e-12, maxit=20000, check_every=1)[1]
+
+
+# ---- general partition by recursive coordinate bisection (partition.py) ------------------------------------------------
+def _general_mesh(name):
+    if name == "tsx":
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "assembly_tsx_p1.npz"))
+        return g["elements"].astype(np.int64), g["coordinates"], fo.tsx_q_mask(g["coordinates"])
+    m = fo.square_mesh_p1(14, 10, 10.0, 7.0)
+    return m["elements"].astype(np.int64), m["coordinates"], m["Q"]
+
+
+@pytest.mark.parametrize("name,world", [("tsx", 2), ("tsx", 3), ("square", 4), ("square", 8)])
+def test_rcb_partition_bookkeeping(name, world):
+    from fem_elastoplasticity_b200.partition import GeneralPartition, rcb
+    el, co, _ = _general_mesh(name)
+    pe = rcb(co[:, el].mean(axis=1), world)
+    sizes = np.bincount(pe, minlength=world)
+    assert sizes.min() >= el.shape[1] // world - 1 and sizes.max() <= -(-el.shape[1] // world) + 1      # balanced element blocks
+    parts = [GeneralPartition(el, co, r, world) for r in range(world)]
+    owned = np.concatenate([p.nodes[:p.n_owned] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(co.shape[1]))                                      # every node owned exactly once
+    assert np.array_equal(np.sort(np.concatenate([p.elems[:p.n_e_owned] for p in parts])), np.arange(el.shape[1]))
+    for p in parts:
+        # owned rows are complete: every element around an owned node is local
+        around = np.flatnonzero(np.isin(el, p.nodes[:p.n_owned]).any(axis=0))
+        assert np.isin(around, p.elems).all()
+        assert np.array_equal(p.nodes[p.elements_local], el[:, p.elems])
+        for s in p.neighbours:                                                                       # send / recv lists pair up
+            q = parts[s]
+            if s in p.send:
+                assert np.array_equal(p.nodes[p.send[s]], q.nodes[q.recv[p.rank]])
+            if s in p.recv:
+                assert (p.recv[s] >= p.n_owned).all() and np.array_equal(p.nodes[p.recv[s]], q.nodes[q.send[p.rank]])
+        ghosts = np.sort(np.concatenate([p.recv[s] for s in p.recv])) if p.recv else np.array([], dtype=np.int64)
+        assert np.array_equal(ghosts, np.arange(p.n_owned, p.n_n_local))                             # every ghost has exactly one source
+    if name == "square" and world == 4:                                                              # 2 x 2 tiles: > 2 neighbours
+        assert max(len(p.neighbours) for p in parts) == 3
+
+
+def _general_worker(rank, world, port, name, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fem_elastoplasticity_b200.distributed import DistributedPCG
+    from fem_elastoplasticity_b200.partition import GeneralPartition
+    el, co, Q = _general_mesh(name)
+    part = GeneralPartition(el, co, rank, world)
+    lm = part.local_mesh({"coordinates": co, "Q": Q}, "cpu")
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    n_e = part.n_e_local
+    K = fo.elastic_stiffness(part.elements_local, lm["coordinates"].numpy(), 3.0 * np.ones(n_e), 5.0 * np.ones(n_e), d1, d2, wf)[0]
+    mask = lm["Q"].t().reshape(-1).to(torch.uint8) & part.owned_mask("cpu")
+    b_global = np.random.default_rng(5).standard_normal(2 * co.shape[1]).reshape(-1, 2)
+    rhs = torch.as_tensor(b_global[part.nodes].reshape(-1).copy())
+    pcg = DistributedPCG(None, part, mask, ops=NumpyOps(K))
+    x, its = pcg.solve(None, rhs, rtol=1e-13, maxit=5000, check_every=10)
+    en = pcg.energy_norms(None, x.clone(), rhs.clone(), x.clone())
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), x=x.numpy(), nodes=part.nodes, n_owned=part.n_owned, its=its, en=en.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("tsx", 2), ("tsx", 3), ("square", 4)])
+def test_rcb_partitioned_pcg_equals_single_domain(tmp_path, name, world):
+    """Jacobi-PCG over the RCB partition (index-list halos with up to 3 neighbours per rank, unstructured tsx mesh) against
+    the single-domain sparse direct solve; ghost entries hold their owners' converged values after the final exchange."""
+    mp.spawn(_general_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    el, co, Q = _general_mesh(name)
+    et = fo.ElementType.P1
+    xi, wf = fo.quadrature_volume(et)
+    _, d1, d2 = fo.local_basis_volume(et, xi)
+    n_e = el.shape[1]
+    K = fo.elastic_stiffness(el, co, 3.0 * np.ones(n_e), 5.0 * np.ones(n_e), d1, d2, wf)[0].tocsr()
+    qf = np.asarray(Q, dtype=bool).flatten(order="F")
+    b = np.random.default_rng(5).standard_normal(K.shape[0])
+    ref = np.zeros_like(b)
+    ref[qf] = spla.spsolve(K[qf][:, qf].tocsc(), b[qf])
+    ref2 = ref.reshape(-1, 2)
+    got = np.full_like(ref2, np.nan)
+    for r in range(world):
+        d = np.load(tmp_path / f"g{r}.npz")
+        x2, nodes, n_own = d["x"].reshape(-1, 2), d["nodes"], int(d["n_owned"])
+        got[nodes[:n_own]] = x2[:n_own]
+        np.testing.assert_allclose(x2, ref2[nodes], rtol=1e-8, atol=1e-10 * np.abs(ref).max())      # ghosts included
+        np.testing.assert_allclose(d["en"][1], b @ (K @ b), rtol=1e-11)
+    assert not np.isnan(got).any()

@@ -260,3 +260,61 @@ def test_multi_gpu_multigrid_matches_single_gpu(tmp_path):
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
         assert abs(int(d0[tag + "_its"]) - its1) <= 1, (tag, int(d0[tag + "_its"]), its1)
     print(f"multigrid PCG iterations: {world} GPUs", int(d0["graph_its"]), "1 GPU", its1)
+
+
+def _rcb_worker(rank, world, port, case, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from fem_elastoplasticity_b200 import newton
+    from fem_elastoplasticity_b200.partition import GeneralPartition
+    if case == "tsx":
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "assembly_tsx_p1.npz"))
+        part = GeneralPartition(g["elements"], g["coordinates"], rank, world)
+        out = newton.tsx_driver(g["coordinates"], g["elements"], pcg_rtol=1e-13, part=part)
+    else:
+        from oracle import fem_oracle as fo
+        m = fo.footing_mesh(1, fo.ElementType.P1)
+        part = GeneralPartition(m["elements"], m["coordinates"], rank, world)
+        lm = part.local_mesh({k: m[k] for k in ("coordinates", "Q", "dirichlet_nodes")}, dev)
+        lm["elements"] = torch.as_tensor(part.elements_local.astype(np.int32)).to(dev)
+        out = newton.footing_driver(lm, max_steps=5, pcg_rtol=1e-13, part=part)
+    np.savez(os.path.join(out_dir, f"{case}{rank}.npz"), U=out["U"][:, :part.n_owned], nodes=part.nodes[:part.n_owned], steps=out["steps"],
+             trace=np.array(out["trace"], dtype=float), neighbours=len(part.neighbours))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["tsx", "footing"])
+def test_rcb_partitioned_newton_matches_single_gpu(tmp_path, case):
+    """The load-stepping Newton loops on a recursive-coordinate-bisection partition (partition.GeneralPartition: index-list
+    halos, any number of neighbours): the unstructured tsx-tunnel mesh and the footing mesh cut into element blocks follow
+    the single-GPU runs - same Newton iterations and plastic-point counts per step, same displacements."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    from fem_elastoplasticity_b200 import newton
+    from oracle import fem_oracle as fo
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    mp.spawn(_rcb_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    if case == "tsx":
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "assembly_tsx_p1.npz"))
+        ref = newton.tsx_driver(g["coordinates"], g["elements"], pcg_rtol=1e-13)
+    else:
+        m = fo.footing_mesh(1, fo.ElementType.P1)
+        ref = newton.footing_driver({k: m[k] for k in ("coordinates", "elements", "Q", "dirichlet_nodes")}, max_steps=5, pcg_rtol=1e-13)
+    U = np.full_like(ref["U"], np.nan)
+    for r in range(world):
+        d = np.load(tmp_path / f"{case}{r}.npz")
+        U[:, d["nodes"]] = d["U"]
+        assert int(d["steps"]) == ref["steps"]
+        tr, rt = d["trace"], np.array(ref["trace"], dtype=float)
+        assert tr.shape == rt.shape and np.array_equal(tr[:, 1:3], rt[:, 1:3])            # Newton iteration index, plastic points
+        np.testing.assert_allclose(tr[:, 3], rt[:, 3], rtol=1e-4, atol=1e-11)             # criteria
+    assert not np.isnan(U).any()
+    err = np.abs(U - ref["U"]).max() / np.abs(ref["U"]).max()
+    print(case, f"RCB partition on {world} GPUs: displacement difference to the single-GPU run", err)
+    assert err <= 1e-9
