@@ -285,6 +285,24 @@ def strong_scaling_part(args, world, rank, dev, d1, d2, wf, pcg_one_gpu_ms=None)
                            f"({'multigrid' if mgs is not None else 'jacobi'} PCG); the one-GPU time of this mesh is ms_per_step of the N=1 run"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU ``index`` (first-touch then places the pinned host
+    buffers on that NUMA node: with every rank on node 0 the end-to-end leg of round 1 did not scale past 1.5x at 8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cores local to GPU {index}"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
@@ -298,6 +316,7 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)   # pinned host buffers of the end-to-end leg are then allocated next to this GPU
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -625,17 +644,26 @@ def run_gpu(args):
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent: pinned host DS -> device -> kernel -> pinned host K values, every step; two steps in flight "
                         "(double-buffered, H2D of step i+1 overlaps D2H of step i)", "steps": e2e_steps},
-        "e2e_step": facade,
+        "e2e_step": facade, "host_numa_binding": numa,
         "gpu_launches": int(launches["n"] * args.steps),
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_pass(args.cpu_nx, args.pcg_iters, 1, 0)
-        line["cpu_baseline"] = {"value": r["n_e"] / r["t"]["tangent"] / 1e6, "unit": "Melem/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle port of Plasticity2D_DP/pythonFEM.py:1047-1050 on {args.cpu_nx}x{args.cpu_nx} cells "
-                                          f"({r['n_e']} elements, 1/{max(1, n_e_tot // r['n_e'])} of the workload); host has {os.cpu_count()} cores, "
-                                          "the reference path is single-threaded",
-                                "return_map_mpts_s": r["n_e"] / r["t"]["return_map"] / 1e6,
-                                "pcg_ms_per_iter": 1e3 * r["t"]["pcg"] / max(args.pcg_iters, 1), "newton_step_s": r["t"]["step"]}
+        # 100 k elements (config 1's size), 0.5 M and 1 M; rates are per element, the largest sample is the headline
+        sizes = []
+        for cnx in sorted({224, args.cpu_nx, 707}):
+            r = cpu_reference_pass(cnx, args.pcg_iters, 1, 0)
+            sizes.append({"n_elements": r["n_e"], "tangent_assembly_melem_s": r["n_e"] / r["t"]["tangent"] / 1e6,
+                          "elastic_assembly_melem_s": r["n_e"] / r["t_elastic"] / 1e6, "return_map_mpts_s": r["n_e"] / r["t"]["return_map"] / 1e6,
+                          "pcg_ms_per_iter": 1e3 * r["t"]["pcg"] / max(args.pcg_iters, 1),
+                          "newton_step_fixed_iterations_s": r["t"]["step"]})
+        line["cpu_baseline"] = {"value": sizes[-1]["tangent_assembly_melem_s"], "unit": "Melem/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle port of Plasticity2D_DP/pythonFEM.py:1047-1050 on {sizes[-1]['n_elements']} elements "
+                                          f"(1/{max(1, n_e_tot // sizes[-1]['n_elements'])} of the workload; the reference's assembly needs ~2.1 KB "
+                                          f"of host memory per element, 34 GB at 16M); host has {os.cpu_count()} cores, the reference path is "
+                                          "single-threaded; port vs the reference itself (build container, 204 800 elements): tangent 1.23 vs 1.28 "
+                                          "Melem/s, return map 1.09 vs 1.65 Mpts/s (BASELINE.md)",
+                                "return_map_mpts_s": sizes[-1]["return_map_mpts_s"], "pcg_ms_per_iter": sizes[-1]["pcg_ms_per_iter"],
+                                "newton_step_s": sizes[-1]["newton_step_fixed_iterations_s"], "sizes": sizes}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

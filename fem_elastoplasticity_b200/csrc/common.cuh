@@ -33,7 +33,7 @@ struct FemTuning {
   int spmv_blocks_per_sm;  // 0 = 32
   int assemble_variant;    // 0 auto, 1 shared-memory accumulators (A), 2 register accumulators (B), 7 one-shot TMA (C), 6 persistent TMA (D), 8 persistent TMA with shared-memory accumulators (E)
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
-  int spmv_staged;         // 0 auto (staged x when the plan has tiles), 1 gather x from global memory (round-1 kernel)
+  int spmv_staged;         // 0 auto (every operand streamed through shared memory when the tiles fit, else as 2), 1 gather x from global memory (round-1 kernel), 2 x staged, matrix through registers
   int peer_timeout_ms;     // bound of the in-kernel waits of the fused multi-GPU PCG (0 = 10 000 ms)
   int strain_variant;      // 0/1 stored gradients (default), 2 P1 gradients recomputed from the coordinates (slower: L2 gathers)
   int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
@@ -102,9 +102,10 @@ struct fem_plan {
   // <= FEM_SPMV_MAXSEG contiguous node ranges (brought into shared memory by bulk async copies), and per 2x2 block the
   // position of its column inside that staged buffer
   int64_t n_tiles;
-  int32_t* tile_seg;   // [n_tiles][FEM_SPMV_DESC]: nseg (0 = gather from global), total nodes, then (start, len) per segment
+  int32_t* tile_seg;   // [n_tiles][FEM_SPMV_DESC]: nseg (0 = gather from global), total nodes, (start, len) per segment, [10] first block, [11] blocks
   uint16_t* nbr_loc;   // [n_blocks]
   int64_t spmv_fallback_tiles;
+  int tile_max_blocks;  // most 2x2 blocks in one tile (the streaming SpMV needs them to fit a shared-memory stage)
   int64_t bytes;
 };
 

@@ -9,6 +9,7 @@
 // through the lattice (no atomics, bit-reproducible).  Everything is HBM-bound FP64 streaming; no tensor cores.
 #include "common.cuh"
 #include "spmv.cuh"
+#include "spmv_stream.cuh"
 #include "peer.cuh"
 
 struct fem_peer_table {
@@ -288,7 +289,7 @@ struct MgFineEpilogue {
 };
 
 template <int GROUP, int MODE, class VT>
-__global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                                          const int32_t* __restrict__ tile_seg, const VT* __restrict__ vals,
                                                                          const double* x, const MgFineEpilogue<MODE> epi, double* dot_out) {
@@ -307,6 +308,58 @@ __global__ void __launch_bounds__(256) mg_fine_rows_kernel(int64_t n_n, const in
                                                            const MgFineEpilogue<MODE> epi, double* dot_out) {
   __shared__ double red[32];
   double dot = spmv_rows_epi<GROUP, 2, MgFineEpilogue<MODE>, VT>(n_n, nbr_ptr, nbr_idx, vals, x, epi);
+  if (dot_out) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+  }
+}
+
+// the same steps for the streaming SpMV (spmv_stream.cuh): b, D^-1, d, x of the tile's nodes arrive in shared memory with
+// the matrix values; the lead lane of a node only computes and stores
+template <int MODE>
+struct MgStreamEpilogue {
+  static constexpr int N_IN = MODE == MG_RESID ? 1 : 4;
+  const double2* b;
+  const double2* dinv;
+  double2* d;
+  const double2* x;
+  double2* out;
+  const uint8_t* mask;
+  double c1, c2;
+  bool want_dot;
+  int64_t own_lo, own_hi;
+  __device__ __forceinline__ const double2* in(int k) const { return k == 0 ? b : (k == 1 ? dinv : (k == 2 ? d : x)); }
+  __device__ __forceinline__ const uint8_t* mask_ptr() const { return MODE == MG_RESID ? mask : nullptr; }
+  __device__ __forceinline__ void operator()(const int64_t a, const double acc0, const double acc1, const double2 (&s)[N_IN], const uchar2 mk,
+                                             double& dot) const {
+    if (a < own_lo || a >= own_hi) return;
+    const double2 bi = s[0];
+    double r0 = bi.x - acc0, r1 = bi.y - acc1;
+    if (MODE == MG_RESID) {
+      if (!mk.x) r0 = 0.0;
+      if (!mk.y) r1 = 0.0;
+      out[a] = make_double2(r0, r1);
+      return;
+    }
+    const double2 di = s[N_IN > 1 ? 1 : 0], dd = s[N_IN > 2 ? 2 : 0], xi = s[N_IN > 3 ? 3 : 0];
+    double2 dn = make_double2(c2 * di.x * r0, c2 * di.y * r1);  // D^-1 is zero on masked DOFs: d and x stay zero there
+    if (c1 != 0.0) {
+      dn.x = fma(c1, dd.x, dn.x);
+      dn.y = fma(c1, dd.y, dn.y);
+    }
+    d[a] = dn;
+    const double2 xo = make_double2(xi.x + dn.x, xi.y + dn.y);
+    out[a] = xo;
+    if (want_dot) dot = fma(bi.x, xo.x, fma(bi.y, xo.y, dot));
+  }
+};
+
+template <int GROUP, int MODE, class VT>
+__global__ void __launch_bounds__(FEM_STREAM_THREADS, 1) mg_fine_stream_kernel(const SpmvStreamArgs A, const VT* __restrict__ vals, const double* x,
+                                                                           const MgStreamEpilogue<MODE> epi, double* dot_out) {
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  __shared__ double red[32];
+  double dot = spmv_stream<GROUP, false, VT>(A, vals, x, epi, stream_smem);
   if (dot_out) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) atomicAdd(dot_out, dot);
@@ -562,6 +615,33 @@ int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const d
                            D->own_node_lo, D->own_node_hi, 0};
   const SpmvShape sh = spmv_shape(P);
   epi.group = sh.group;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                         reinterpret_cast<uintptr_t>(D->dinv) | reinterpret_cast<uintptr_t>(D->d) | reinterpret_cast<uintptr_t>(D->mask)) & 15u) == 0;
+  // default: every operand streamed through shared memory by a producer warp (FP32 values: three stages, 0.352 ms per
+  // Chebyshev step at 16M elements against 0.569 ms of the register-fed kernel below)
+  if (g_fem_tuning.spmv_staged == 0 && spmv_can_stream(P) && aligned) {
+    const SpmvStreamArgs A{P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg};
+    const MgStreamEpilogue<MODE> se{reinterpret_cast<const double2*>(b), reinterpret_cast<const double2*>(D->dinv), reinterpret_cast<double2*>(D->d),
+                                    reinterpret_cast<const double2*>(x), reinterpret_cast<double2*>(out), D->mask, c1, c2, dot != nullptr,
+                                    D->own_node_lo, D->own_node_hi};
+    constexpr int smem = SpmvStreamSmem<VT>::TOTAL;
+    const unsigned sb = spmv_stream_blocks(P);
+#define MGS(G)                                                                                                              \
+  do {                                                                                                                      \
+    static bool attr_set = false;                                                                                           \
+    if (!attr_set) {                                                                                                        \
+      FEM_CUDA_CHECK(cudaFuncSetAttribute(mg_fine_stream_kernel<G, MODE, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_set = true;                                                                                                      \
+    }                                                                                                                       \
+    mg_fine_stream_kernel<G, MODE, VT><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K, x, se, dot);                               \
+  } while (0)
+    if (sh.group == 4) MGS(4);
+    else if (sh.group == 8) MGS(8);
+    else MGS(16);
+#undef MGS
+    FEM_CUDA_CHECK(cudaGetLastError());
+    return FEM_OK;
+  }
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
 #define MGT(G) mg_fine_tiles_kernel<G, MODE, VT><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot)

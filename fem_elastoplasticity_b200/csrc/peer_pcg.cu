@@ -58,7 +58,7 @@ struct PeerView {
 // neighbour GPUs while this kernel is already resident (it spins on the halo flags), so every load of p is a coherent
 // one (bulk async copies after a proxy fence, or ld.global.cg in the gather fallback).
 template <int GROUP>
-__global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) ppcg_spmv_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS) ppcg_spmv_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                         const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                         const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                         const double* p, double* __restrict__ q,

@@ -512,6 +512,11 @@ __global__ void __launch_bounds__(FEM_SPMV_TILE) build_spmv_tiles(int64_t n_n, c
       d[2 + 2 * k] = (ok && k < nseg) ? s_start[k] : 0;
       d[3 + 2 * k] = (ok && k < nseg) ? s_len[k] : 0;
     }
+    // block range of the tile (its matrix values and positions are contiguous): streamed as one copy each (spmv_stream.cuh)
+    const int64_t a0 = tile * FEM_SPMV_TILE, a1 = (a0 + FEM_SPMV_TILE < n_n) ? a0 + FEM_SPMV_TILE : n_n;
+    d[10] = nbr_ptr[a0];
+    d[11] = nbr_ptr[a1] - nbr_ptr[a0];
+    atomicMax(n_fallback + 1, d[11]);
     s_nseg = ok ? nseg : 0;
     if (!ok && hi >= lo) atomicAdd(n_fallback, 1);
   }
@@ -658,16 +663,18 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     // x-staging plan of the SpMV
     P->n_tiles = (n_n + FEM_SPMV_TILE - 1) / FEM_SPMV_TILE;
     if ((rc = dmalloc(P, &P->tile_seg, P->n_tiles * FEM_SPMV_DESC)) != FEM_OK) break;
-    if ((rc = dmalloc(P, &P->nbr_loc, n_blocks)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->nbr_loc, n_blocks + 16)) != FEM_OK) break;  // + slack: the streamed copies are rounded to 16 bytes
     {
-      int* nfb = nullptr;
-      if (cudaMalloc(&nfb, sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc nfb"); break; }
-      cudaMemsetAsync(nfb, 0, sizeof(int), st);
+      int* nfb = nullptr;  // [0] tiles whose x ranges do not fit, [1] most blocks in one tile
+      if (cudaMalloc(&nfb, 2 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc nfb"); break; }
+      cudaMemsetAsync(nfb, 0, 2 * sizeof(int), st);
+      cudaMemsetAsync(P->nbr_loc + n_blocks, 0, 16 * sizeof(uint16_t), st);
       build_spmv_tiles<<<(unsigned)P->n_tiles, FEM_SPMV_TILE, 0, st>>>(n_n, P->nbr_ptr, P->nbr_idx, P->tile_seg, P->nbr_loc, nfb);
-      int h_nfb = 0;
-      cudaMemcpy(&h_nfb, nfb, sizeof(int), cudaMemcpyDeviceToHost);
+      int h_nfb[2] = {0, 0};
+      cudaMemcpy(h_nfb, nfb, sizeof(h_nfb), cudaMemcpyDeviceToHost);
       cudaFree(nfb);
-      P->spmv_fallback_tiles = h_nfb;
+      P->spmv_fallback_tiles = h_nfb[0];
+      P->tile_max_blocks = h_nfb[1];
     }
     // SELL-32 incidence storage
     P->n_slices = (n_n + 31) / 32;

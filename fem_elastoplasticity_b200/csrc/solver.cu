@@ -9,6 +9,7 @@
 // gathered as one double2 per block through L1/L2.
 #include "common.cuh"
 #include "spmv.cuh"
+#include "spmv_stream.cuh"
 
 template <int GROUP, int U>
 __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
 
 // x staged through shared memory by bulk async copies (spmv.cuh: spmv_tiles)
 template <int GROUP>
-__global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
+__global__ void __launch_bounds__(FEM_SPMV_THREADS) spmv_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                          const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                          const double* __restrict__ x, double* __restrict__ y,
@@ -48,12 +49,52 @@ __global__ void __launch_bounds__(FEM_SPMV_THREADS, 2) spmv_tiles_kernel(int64_t
   }
 }
 
+// every operand streamed through shared memory by bulk async copies (spmv_stream.cuh); one persistent CTA per SM
+template <int GROUP>
+__global__ void __launch_bounds__(FEM_STREAM_THREADS, 1) spmv_stream_kernel(const SpmvStreamArgs A, const double* __restrict__ vals, const double* __restrict__ x,
+                                                                        const SpmvStreamStore epi, double* dot_out, double* zero_a, double* zero_b) {
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  __shared__ double red[32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (zero_a) *zero_a = 0.0;
+    if (zero_b) *zero_b = 0.0;
+  }
+  double dot = spmv_stream<GROUP, false, double>(A, vals, x, epi, stream_smem);
+  if (dot_out) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+  }
+}
+
 static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x, double* y, const uint8_t* mask,
                        double* dot, double* zero_a, double* zero_b, cudaStream_t st) {
   FEM_REQUIRE((reinterpret_cast<uintptr_t>(K_vals) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 &&
                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
   const SpmvShape sh = spmv_shape(P);
   const int threads = 256, group = sh.group, unroll = sh.unroll;
+  // default: every operand streamed through shared memory by a producer warp (0.380 ms at 16M elements; the register-fed
+  // kernel below: 0.455 ms; tuning key spmv_staged = 2 selects it, 1 the round-1 gather kernel)
+  if (g_fem_tuning.spmv_staged == 0 && spmv_can_stream(P) && (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15u) == 0)) {
+    const SpmvStreamArgs A{P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg};
+    const SpmvStreamStore epi{y, mask, x, dot != nullptr};
+    constexpr int smem = SpmvStreamSmem<double>::TOTAL;
+    const unsigned sb = spmv_stream_blocks(P);
+#define SPMVS(G)                                                                                                  \
+  do {                                                                                                            \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      FEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_stream_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    spmv_stream_kernel<G><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K_vals, x, epi, dot, zero_a, zero_b);            \
+  } while (0)
+    if (group == 4) SPMVS(4);
+    else if (group == 8) SPMVS(8);
+    else SPMVS(16);
+#undef SPMVS
+    FEM_CUDA_CHECK(cudaGetLastError());
+    return FEM_OK;
+  }
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
 #define SPMVT(G) spmv_tiles_kernel<G><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b)

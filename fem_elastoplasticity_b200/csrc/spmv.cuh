@@ -82,12 +82,7 @@ __device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t
       }
     }
     int m[U];
-    double2 v0[U], v1[U], xv[U], pf[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t a = nb + u * GPW + gi;
-      pf[u] = (a < n_n) ? epi.prefetch(a, sub) : make_double2(0.0, 0.0);
-    }
+    double2 v0[U], v1[U], xv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       m[u] = 0;
@@ -126,7 +121,7 @@ __device__ __forceinline__ double spmv_rows_epi(const int64_t n_n, const int32_t
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
       }
       const int64_t a = nb + u * GPW + gi;
-      epi(a, sub == 0 && a < n_n, acc0, acc1, dot, pf[u]);
+      epi(a, sub == 0 && a < n_n, acc0, acc1, dot, (a < n_n) ? epi.prefetch(a, sub) : make_double2(0.0, 0.0));
     }
   }
   return dot;
@@ -213,65 +208,43 @@ __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_
   uint32_t phase[2] = {0u, 0u};
   double dot = 0.0;
   int it = 0;
-  using P2 = typename SpmvPair<VT>::type;
-  // Row extents (and the staged/gather switch) of a sweep are fetched one sweep ahead, so that a sweep starts with its
-  // matrix loads instead of a dependent look-up: one global round trip per tile instead of three.
-  auto row_info = [&](const int64_t tile, const int sw, int (&p0)[U], int (&deg)[U], bool& staged) {
-    staged = false;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      p0[u] = 0;
-      deg[u] = 0;
-    }
-    if (tile >= n_tiles) return;
-    staged = __ldg(tile_seg + tile * FEM_SPMV_DESC) > 0;  // CTA-uniform
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
-      if (a < n_n) {
-        p0[u] = __ldg(nbr_ptr + a);
-        deg[u] = __ldg(nbr_ptr + a + 1) - p0[u];
-      }
-    }
-  };
-  int p0[U], deg[U];
-  bool staged;
-  row_info(blockIdx.x, 0, p0, deg, staged);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int cur = it & 1;
     const int64_t next = tile + gridDim.x;
     if (threadIdx.x == 0 && next < n_tiles) spmv_issue_tile(tile_seg, next, x, sm.xbuf[cur ^ 1], &sm.bar[cur ^ 1]);
-    const bool tile_staged = staged;
+    const bool staged = tile_seg[tile * FEM_SPMV_DESC] > 0;  // CTA-uniform
     const double2* xs = sm.xbuf[cur];
     bool waited = false;
 #pragma unroll 1
     for (int sw = 0; sw < SWEEPS; ++sw) {
+      int p0[U], deg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
+        p0[u] = 0;
+        deg[u] = 0;
+        if (a < n_n) {
+          p0[u] = __ldg(nbr_ptr + a);
+          deg[u] = __ldg(nbr_ptr + a + 1) - p0[u];
+        }
+      }
       int m[U][B];
-      P2 v0[U][B], v1[U][B];
-      double2 pf[U];
+      double2 v0[U][B], v1[U][B];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           const int j = sub + b * GROUP;
           m[u][b] = 0;
-          v0[u][b].x = v0[u][b].y = v1[u][b].x = v1[u][b].y = 0;
+          v0[u][b] = v1[u][b] = make_double2(0.0, 0.0);
           if (j < deg[u]) {
+            using P2 = typename SpmvPair<VT>::type;
             const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
             m[u][b] = staged ? (int)__ldcs(nbr_loc + p0[u] + j) : __ldg(nbr_idx + p0[u] + j);
-            v0[u][b] = __ldcs(row0 + j);
-            v1[u][b] = __ldcs(row0 + deg[u] + j);
+            v0[u][b] = spmv_ld_pair<VT>(row0 + j);
+            v1[u][b] = spmv_ld_pair<VT>(row0 + deg[u] + j);
           }
         }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
-        pf[u] = (a < n_n) ? epi.prefetch(a, sub) : make_double2(0.0, 0.0);
-      }
-      int p0n[U], degn[U];
-      bool stagedn;
-      if (sw + 1 < SWEEPS) row_info(tile, sw + 1, p0n, degn, stagedn);
-      else row_info(next, 0, p0n, degn, stagedn);
       if (staged && !waited) {  // the matrix values above are in flight while the x ranges arrive
         spmv_bar_wait(&sm.bar[cur], phase[cur]);
         waited = true;
@@ -284,13 +257,14 @@ __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_
           const int j = sub + b * GROUP;
           if (j < deg[u]) {
             const double2 xv = staged ? xs[m[u][b]] : spmv_ldx<COHERENT>(x, m[u][b]);
-            acc0 = fma((double)v0[u][b].x, xv.x, acc0);
-            acc0 = fma((double)v0[u][b].y, xv.y, acc0);
-            acc1 = fma((double)v1[u][b].x, xv.x, acc1);
-            acc1 = fma((double)v1[u][b].y, xv.y, acc1);
+            acc0 = fma(v0[u][b].x, xv.x, acc0);
+            acc0 = fma(v0[u][b].y, xv.y, acc0);
+            acc1 = fma(v1[u][b].x, xv.x, acc1);
+            acc1 = fma(v1[u][b].y, xv.y, acc1);
           }
         }
         for (int j = sub + B * GROUP; j < deg[u]; j += GROUP) {  // rows longer than B*GROUP blocks
+          using P2 = typename SpmvPair<VT>::type;
           const P2* row0 = reinterpret_cast<const P2*>(vals + 4 * (int64_t)p0[u]);
           const double2 w0 = spmv_ld_pair<VT>(row0 + j), w1 = spmv_ld_pair<VT>(row0 + deg[u] + j);
           const double2 xx = staged ? xs[__ldcs(nbr_loc + p0[u] + j)] : spmv_ldx<COHERENT>(x, __ldg(nbr_idx + p0[u] + j));
@@ -305,16 +279,10 @@ __device__ __forceinline__ double spmv_tiles_epi(const int64_t n_n, const int64_
           acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
         }
         const int64_t a = tile * FEM_SPMV_TILE + sw * NPS + u * GPC + gi;
-        epi(a, sub == 0 && a < n_n, acc0, acc1, dot, pf[u]);
+        epi(a, sub == 0 && a < n_n, acc0, acc1, dot, (a < n_n) ? epi.prefetch(a, sub) : make_double2(0.0, 0.0));
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        p0[u] = p0n[u];
-        deg[u] = degn[u];
-      }
-      staged = stagedn;
     }
-    if (tile_staged) {
+    if (staged) {
       if (!waited) spmv_bar_wait(&sm.bar[cur], phase[cur]);
       phase[cur] ^= 1u;
     }

@@ -138,3 +138,47 @@ def test_newton_drivers_with_multigrid(golden):
     err = np.abs(out["U"] - oref["U"]).max() / np.abs(oref["U"]).max()
     print("footing L1 with multigrid: displacement error vs dense-LU oracle", err, "PCG iterations", [t[4] for t in out["trace"]][:8])
     assert err <= 1e-9
+
+
+def test_fine_step_code_paths_agree(fem):
+    """The level-0 multigrid step through its three SpMV code paths - all operands streamed through shared memory by bulk
+    copies (default), x staged + matrix through registers, everything gathered - with the FP64 matrix and its FP32 copy:
+    same results to rounding, and the FP64 one equal to the plain formulas."""
+    torch, mg = fem["torch"], fem["mg"]
+    from fem_elastoplasticity_b200 import _lib
+    d1, d2, wf = p1_tables()
+    m = fem["meshgen"].square_mesh_p1(333, 211, 10.0, 6.0)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    G, Kb, _, _ = fem["meshgen"].footing_materials(P.n_int)
+    k = P.assemble_elastic(G, Kb)
+    mask = P.mask_u8(m["Q"])
+    g = torch.Generator(device="cuda").manual_seed(4)
+    rnd = lambda: torch.randn(P.n_dof, dtype=torch.float64, device="cuda", generator=g) * mask  # noqa: E731
+    b, x = rnd(), rnd()
+    for f32 in (False, True):
+        M = mg.MultigridPCG(P, mask, smoother_f32=f32).setup(k)
+        P.jacobi(k, mask, out=M.minv)
+        if f32:
+            _lib.call("fem_mg_to_f32", P.nnz, fem["plan"]._ptr(k), fem["plan"]._ptr(M.k32), fem["plan"]._stream())
+        d0 = rnd()
+        outs = []
+        try:
+            for staged in (0, 2, 1):
+                _lib.call("fem_set_tuning", b"spmv_staged", staged)
+                M.v0["d"].copy_(d0)
+                out, res, dot = torch.zeros_like(x), torch.zeros_like(x), torch.zeros(1, dtype=torch.float64, device="cuda")
+                M.fine_step(k, b, x, out, mode=2, step=1, dot=dot)
+                M.fine_step(k, b, x, res, mode=1)
+                outs.append((out.clone(), M.v0["d"].clone(), res.clone(), float(dot.item())))
+        finally:
+            _lib.call("fem_set_tuning", b"spmv_staged", 0)
+        for o in outs[1:]:
+            for a, c in zip(outs[0][:3], o[:3]):
+                assert float((a - c).abs().max()) <= 1e-12 * float(c.abs().max())
+            assert abs(outs[0][3] - o[3]) <= 1e-11 * abs(o[3])
+        r_ref = (b - P.spmv(k, x)) * mask
+        d_ref = M.desc.c1[1] * d0 + M.desc.c2[1] * M.minv * r_ref
+        tol = 1e-12 if not f32 else 1e-6
+        assert float((outs[0][2] - r_ref).abs().max()) <= tol * float(r_ref.abs().max())
+        assert float((outs[0][1] - d_ref).abs().max()) <= tol * float(d_ref.abs().max())
+        assert float((outs[0][0] - (x + d_ref)).abs().max()) <= tol * float((x + d_ref).abs().max())

@@ -78,15 +78,17 @@ def main():
     mask = P.mask_u8(m["Q"])
     dot = torch.zeros(1, dtype=torch.float64, device="cuda")
     y_ref = None
-    for staged in (1, 0):                                # 1: round-1 kernel (x gathered through L1/L2); 0: x staged in shared memory
+    # 1: round-1 kernel (x gathered through L1/L2); 2: x staged in shared memory, matrix through registers; 0: every operand
+    # streamed through shared memory by bulk async copies (one persistent CTA per SM)
+    for staged, name, bpss in ((1, "gather", (8,)), (2, "staged", (2,)), (0, "stream", (1,))):
         knob("spmv_staged", staged)
-        for bps in ((8,) if staged else (1, 2, 3, 4)):
+        for bps in bpss:
             knob("spmv_blocks_per_sm", bps)
-            res[f"spmv_{'gather' if staged else 'staged'}_b{bps}_ms"] = timeit(lambda: P.spmv(kel_ref, u, mask=mask, out=y, dot=dot))
+            res[f"spmv_{name}_b{bps}_ms"] = timeit(lambda: P.spmv(kel_ref, u, mask=mask, out=y, dot=dot))
             if y_ref is None:
                 y_ref = y.clone()
             else:
-                res[f"spmv_{'gather' if staged else 'staged'}_b{bps}_maxdiff"] = float((y - y_ref).abs().max() / y_ref.abs().max())
+                res[f"spmv_{name}_b{bps}_maxdiff"] = float((y - y_ref).abs().max() / y_ref.abs().max())
     knob("spmv_staged", 0), knob("spmv_blocks_per_sm", 0)
     for w in (4, 5, 6, 8, 10, 11):                       # warps per CTA of the persistent register-accumulator kernel (D)
         knob("assemble_variant", 6), knob("assemble_warps", w)
