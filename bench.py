@@ -592,10 +592,10 @@ def run_gpu(args):
         # the dominant kernel of the converged step: the level-0 Chebyshev step of the V-cycle (2*degree - 1 launches per CG
         # iteration), the smoother's vector updates fused into the epilogue of the block-CSR SpMV
         n_cheb = (2 * mgs.degree - 1) * int(solve_info["iterations"]) + 2 * mgs.degree - 1
-        roof = {"bound": "hbm", "kernel": "mg_fine_tiles_kernel<CHEB> (level-0 Chebyshev smoothing step of the multigrid V-cycle: block-CSR SpMV on the "
+        roof = {"bound": "hbm", "kernel": "mg_fine_stream_kernel<CHEB> (level-0 Chebyshev smoothing step of the multigrid V-cycle: block-CSR SpMV streamed through shared memory by a producer warp, "
                                           f"{'FP32' if mgs.k32 is not None else 'FP64'} matrix copy + fused vector updates)",
                 "achieved": gbs(algo["mg_cheb"], t_mg_cheb), "peak": peak, "unit": "GB/s", "frac": gbs(algo["mg_cheb"], t_mg_cheb) / peak,
-                "traffic": ncu_traffic.get("mg_fine_tiles_kernel_cheb"), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["mg_cheb"],
+                "traffic": ncu_traffic.get("mg_fine_stream_kernel_cheb"), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo["mg_cheb"],
                 "ms_per_launch": t_mg_cheb, "launches_per_step": n_cheb, "share_of_step": n_cheb * t_mg_cheb / ms_step,
                 "frac_of_8TBs_nominal": gbs(algo["mg_cheb"], t_mg_cheb) / 8000.0,
                 "assembly": asm_roof}

@@ -180,8 +180,8 @@ __global__ void mg_stencil_to_dense_kernel(Geom g, const double* __restrict__ S,
 // ---- smoother / residual on a structured level ------------------------------------------------------------------------
 enum { MG_APPLY = 0, MG_RESID = 1, MG_CHEB = 2, MG_FIRST = 3 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) mg_stencil_kernel(Geom g, int row_lo, int row_hi, const double* __restrict__ S, const double2* x,
+template <int MODE, class ST>
+__global__ void __launch_bounds__(256) mg_stencil_kernel(Geom g, int row_lo, int row_hi, const ST* __restrict__ S, const double2* x,
                                                          const double2* __restrict__ b, const double2* __restrict__ dinv, double2* d,
                                                          double2* out, double c1, double c2) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(256) mg_stencil_kernel(Geom g, int row_lo, int
     const int dx = s % 3 - 1, dy = s / 3 - 1;
     const bool v = (i + dx >= 0) && (i + dx < g.nxn) && (j + dy >= 0) && (j + dy < g.nrows);
     const double2 xv = v ? x[node + dy * g.nxn + dx] : make_double2(0.0, 0.0);
-    const double* sp = S + (int64_t)(4 * s) * g.n + node;
-    y0 = fma(__ldcs(sp), xv.x, y0);
-    y0 = fma(__ldcs(sp + g.n), xv.y, y0);
-    y1 = fma(__ldcs(sp + 2 * g.n), xv.x, y1);
-    y1 = fma(__ldcs(sp + 3 * g.n), xv.y, y1);
+    const ST* sp = S + (int64_t)(4 * s) * g.n + node;
+    y0 = fma((double)__ldcs(sp), xv.x, y0);
+    y0 = fma((double)__ldcs(sp + g.n), xv.y, y0);
+    y1 = fma((double)__ldcs(sp + 2 * g.n), xv.x, y1);
+    y1 = fma((double)__ldcs(sp + 3 * g.n), xv.y, y1);
   }
   if (MODE == MG_APPLY) {
     out[node] = make_double2(y0, y1);
@@ -600,9 +600,14 @@ int launch_stencil(const fem_mg_level& L, const double* x, double* out, double c
   const Geom g = geom_of(L);
   const int64_t items = (int64_t)(L.own_hi - L.own_lo) * L.nxn;
   if (items <= 0) return FEM_OK;
-  mg_stencil_kernel<MODE><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, L.S, reinterpret_cast<const double2*>(x),
-                                                           reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv),
-                                                           reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2);
+  if (L.S32 && MODE != MG_FIRST)
+    mg_stencil_kernel<MODE, float><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, L.S32, reinterpret_cast<const double2*>(x),
+                                                                    reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv),
+                                                                    reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2);
+  else
+    mg_stencil_kernel<MODE, double><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, L.S, reinterpret_cast<const double2*>(x),
+                                                                     reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv),
+                                                                     reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -788,7 +793,7 @@ extern "C" int fem_mg_stencil_apply(int nxn, int nrows, int row_lo, int row_hi, 
   const Geom g{nxn, nrows, 0, nrows, (int64_t)nxn * nrows};
   const int64_t items = (int64_t)(row_hi - row_lo) * nxn;
   if (items <= 0) return FEM_OK;
-  mg_stencil_kernel<MG_APPLY><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(g, row_lo, row_hi, S, reinterpret_cast<const double2*>(x), nullptr,
+  mg_stencil_kernel<MG_APPLY, double><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(g, row_lo, row_hi, S, reinterpret_cast<const double2*>(x), nullptr,
                                                                                  nullptr, nullptr, reinterpret_cast<double2*>(y), 0.0, 0.0);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;

@@ -35,7 +35,7 @@ class Exchange(C.Structure):
 class Level(C.Structure):
     _fields_ = [("nxn", C.c_int32), ("nrows", C.c_int32), ("g0", C.c_int32), ("own_lo", C.c_int32), ("own_hi", C.c_int32),
                 ("nrows_global", C.c_int32), ("res_lo", C.c_int32), ("res_hi", C.c_int32),
-                ("S", C.c_void_p), ("dinv", C.c_void_p), ("b", C.c_void_p), ("xa", C.c_void_p), ("xb", C.c_void_p), ("d", C.c_void_p),
+                ("S", C.c_void_p), ("S32", C.c_void_p), ("dinv", C.c_void_p), ("b", C.c_void_p), ("xa", C.c_void_p), ("xb", C.c_void_p), ("d", C.c_void_p),
                 ("r", C.c_void_p), ("c1", C.c_double * MAX_DEGREE), ("c2", C.c_double * MAX_DEGREE),
                 ("ex_xa", Exchange), ("ex_xb", Exchange), ("ex_r", Exchange), ("ex_b", Exchange)]
 
@@ -65,14 +65,16 @@ def chebyshev_coefficients(lmax, ratio, degree):
     return c1, c2
 
 
-def level_layouts(LX, NY, owned, max_coarse_dofs=2500, min_owned_rows=3, max_levels=MAX_LEVELS):
+def level_layouts(LX, NY, owned, max_coarse_dofs=2500, min_owned_rows=3, max_levels=MAX_LEVELS, replicate_below=50000):
     """Layouts of the structured levels l = 1 .. L over an LX x NY node lattice whose rows are owned by the ranks as the
     half-open global ranges ``owned`` (one per rank, ascending, covering [0, NY)).
 
     Level l+1 keeps every second lattice point of level l (ceil: an odd cell count adds one coarse node row/column beyond
     the last fine one).  Coarse row J belongs to the owner of fine row 2J (the last rank takes the extra row).  A level is
-    DISTRIBUTED while every rank owns at least ``min_owned_rows`` rows: its local arrays hold the owned rows plus one ghost
-    row on each side that exists.  Below that, and always on the last (densely solved) level, the level is REPLICATED:
+    DISTRIBUTED while every rank owns at least ``min_owned_rows`` rows and the level has more than ``replicate_below`` nodes
+    (smaller levels are launch-latency bound: computing them redundantly costs nothing and saves ~7 exchanges per level and
+    V-cycle): its local arrays hold the owned rows plus one ghost row on each side that exists.  Below that, and always on
+    the last (densely solved) level, the level is REPLICATED:
     every rank holds all rows; on the first replicated level a rank restricts only its share ``res`` of the rows and the
     shares are gathered.  Returns a list of dicts: nxn, nrows_global, replicated, ranks = [(g0, nrows, own_lo, own_hi,
     res_lo, res_hi)] in local row indices."""
@@ -83,7 +85,7 @@ def level_layouts(LX, NY, owned, max_coarse_dofs=2500, min_owned_rows=3, max_lev
         nxn_c, N_c = -(-(nxn - 1) // 2) + 1, -(-(N - 1) // 2) + 1
         share = [(-(-lo // 2), N_c if hi == N else -(-hi // 2)) for lo, hi in own]
         last = 2 * nxn_c * N_c <= max_coarse_dofs or len(levels) == max_levels - 1 or (nxn_c <= 2 and N_c <= 2)
-        rep = replicated or last or min(hi - lo for lo, hi in share) < min_owned_rows
+        rep = replicated or last or min(hi - lo for lo, hi in share) < min_owned_rows or nxn_c * N_c <= replicate_below
         ranks = []
         for lo, hi in share:
             if rep:
@@ -443,6 +445,9 @@ class MultigridPCG:
             L.nxn, L.nrows, L.g0, L.own_lo, L.own_hi, L.nrows_global = lv["nxn"], lv["nrows"], lv["g0"], lv["own"][0], lv["own"][1], lv["N"]
             L.res_lo, L.res_hi = lv["res"]
             L.S, L.dinv = lv["S"].data_ptr(), lv["dinv"].data_ptr()
+            if self.k32 is not None and li < self.n_levels - 1:     # FP32 copy of the stencil for the smoother (as on level 0)
+                lv["S32"] = lv["S"].to(torch.float32)
+                L.S32 = lv["S32"].data_ptr()
             L.b, L.xa, L.xb, L.d, L.r = (lv[k].data_ptr() for k in ("b", "xa", "xb", "d", "r"))
             if lv["lmax"] is not None:
                 c1, c2 = chebyshev_coefficients(lv["lmax"], self.ratio, self.degree)
@@ -538,7 +543,17 @@ class MultigridPCG:
         bb = float(h[4])
         if iters is None and (bb == 0.0 or float(h[1]) <= rtol * rtol * bb):
             return self.x, 0, 0.0 if bb == 0.0 else (float(h[1]) / bb) ** 0.5
-        graph = self._pair_graph(k_vals) if (self.use_graph and n_it >= 4) else None
+        graph = None
+        if self.use_graph and n_it >= 4:
+            if self._graph is None or self._graph_key != k_vals.data_ptr():
+                # iterations 0 and 1 run eagerly (they count), then the same pair is captured - capturing does not execute.
+                # (No save / restore of the iterates around a warm-up: writing this rank's ghost rows of p back would race
+                # with the neighbours' peer stores into them.)
+                self._iteration(k_vals, 0)
+                self._iteration(k_vals, 1)
+                it = 2
+                self._capture_pair(k_vals)
+            graph = self._graph
         self.launches_last = 0
         while it < n_it:
             nxt = n_it if iters is not None else min(n_it, (it // check_every + 1) * check_every)
@@ -564,25 +579,16 @@ class MultigridPCG:
             raise PCGNotConverged("multigrid PCG", it, rel, rtol)
         return self.x, it, rel
 
-    def _pair_graph(self, k_vals):
-        """CUDA graph of iterations (0, 1): the kernels depend only on the parity of the iteration index."""
-        key = k_vals.data_ptr()
-        if self._graph is not None and self._graph_key == key:
-            return self._graph
+    def _capture_pair(self, k_vals):
+        """CUDA graph of an (even, odd) iteration pair: the kernels depend only on the parity of the iteration index, and
+        every exchange counter lives on the device, so one graph serves the whole solve (and later solves with the same
+        matrix buffer).  Called right after the same two iterations ran eagerly (modules loaded, nothing lazy left)."""
         try:
-            keep = (self.x, self.r, self.p, self.q, self.z, self.scal)
-            saved = [t.clone() for t in keep]
-            self._iteration(k_vals, 0)
-            self._iteration(k_vals, 1)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._iteration(k_vals, 0)
                 self._iteration(k_vals, 1)
-            for t, sv in zip(keep, saved):
-                t.copy_(sv)
-            torch.cuda.synchronize()
-            self._graph, self._graph_key = g, key
+            self._graph, self._graph_key = g, k_vals.data_ptr()
         except Exception as e:                            # capture unsupported: eager launches
             self.graph_error, self.use_graph, self._graph = repr(e), False, None
-        return self._graph

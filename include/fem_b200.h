@@ -230,6 +230,7 @@ typedef struct fem_mg_level {
   int32_t res_lo, res_hi;                               /* local rows of b this rank computes by restriction (= owned rows on a
                                                            distributed level; its share of the rows on the first replicated level) */
   const double* S;                                      /* [36][nxn*nrows] */
+  const float* S32;                                     /* optional FP32 copy of S streamed by the smoother / residual (NULL: use S) */
   const double* dinv;                                   /* [2*nxn*nrows] */
   double *b, *xa, *xb, *d, *r;                          /* work vectors, [2*nxn*nrows] */
   double c1[FEM_MG_MAX_DEGREE], c2[FEM_MG_MAX_DEGREE];  /* Chebyshev recurrence d = c1 d + c2 D^-1 r */

@@ -26,7 +26,10 @@ def test_level_layouts_cover_what_the_kernels_read(nx, ny, world):
         N, nxn = lay["nrows_global"], lay["nxn"]
         assert nxn == -(-(f_nxn - 1) // 2) + 1 and N == -(-(f_N - 1) // 2) + 1
         share = lay["owned_global"]
-        assert share[0][0] == 0 and share[-1][1] == N and all(share[i][1] == share[i + 1][0] for i in range(world - 1))
+        if f_rep:                                          # below a replicated level every rank holds (and computes) all rows
+            assert all(sh == (0, N) for sh in share)
+        else:
+            assert share[0][0] == 0 and share[-1][1] == N and all(share[i][1] == share[i + 1][0] for i in range(world - 1))
         for rk, (g0, nrows, olo, ohi, rlo, rhi) in enumerate(lay["ranks"]):
             assert 0 <= olo < ohi <= nrows and 0 <= rlo <= rhi <= nrows and g0 + nrows <= N
             if lay["replicated"]:
