@@ -699,7 +699,7 @@ def main():
                     help="linear solve of the step: multigrid = CG + V-cycle to --rtol (a converged Newton step); jacobi = --pcg-iters fixed iterations")
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--mg-degree", type=int, default=2)
-    ap.add_argument("--mg-ratio", type=float, default=8.0)
+    ap.add_argument("--mg-ratio", type=float, default=16.0)
     ap.add_argument("--no-facade-step", action="store_true", help="skip the whole-step timing through the pythonFEM facade (one GPU)")
     ap.add_argument("--facade-synthetic-strain", action="store_true", default=True, help=argparse.SUPPRESS)
     ap.add_argument("--two-level", action="store_true", help="also solve the step's system with the two-level preconditioner of round 1")

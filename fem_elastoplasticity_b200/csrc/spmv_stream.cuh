@@ -25,7 +25,7 @@
 
 #define FEM_STREAM_THREADS (FEM_SPMV_THREADS + 32)  // 16 consumer warps + 1 producer warp
 #define FEM_STREAM_VCAP 2048  // 2x2 blocks per stage (a P1 tile holds ~1 800)
-#define FEM_STREAM_NIN 4      // node vectors (one double2 per node) an epilogue can have staged
+#define FEM_STREAM_NIN 5      // node vectors (one double2 per node) an epilogue can have staged
 
 // Epilogue concept:
 //   static constexpr int N_IN          node vectors staged per tile (<= FEM_STREAM_NIN)

@@ -131,7 +131,7 @@ class MultigridPCG:
     operators (Galerkin) from ``k_vals`` - for the Newton loop the elastic matrix, kept for every tangent solve: level 0
     always uses the matrix being solved.  ``solve`` mirrors TwoLevelPCG.solve."""
 
-    def __init__(self, plan, mask, part=None, free_mask=None, degree=2, ratio=8.0, max_coarse_dofs=2500, lattice=None, use_graph=True,
+    def __init__(self, plan, mask, part=None, free_mask=None, degree=2, ratio=16.0, max_coarse_dofs=2500, lattice=None, use_graph=True,
                  smoother_f32=True):
         check_abi()
         self.plan, self.mask = plan, mask
@@ -182,7 +182,8 @@ class MultigridPCG:
         if self.part is not None:
             self._make_arena(n)
         a = self._vec
-        self.r, self.q, self.x, self.z, self.minv = (z(n) for _ in range(5))
+        self.r, self.q, self.x, self.z = (z(n) for _ in range(4))
+        self.minv = z(2 * n)                              # inverse 2x2 diagonal blocks of the matrix being solved, two planes
         self.p = a("p", n)
         self.scal = z(8)
         self.v0 = {"xa": a("xa0", n), "xb": a("xb0", n), "d": z(n), "r": a("r0", n)}
@@ -192,7 +193,7 @@ class MultigridPCG:
             nn = lay["nxn"] * nrows
             self.lv.append({"nxn": lay["nxn"], "nrows": nrows, "g0": g0l, "own": (own_lo, own_hi), "res": (res_lo, res_hi), "n": nn,
                             "N": lay["nrows_global"], "rep": lay["replicated"], "first_rep": lay["first_replicated"],
-                            "S": z(36 * nn), "dinv": z(2 * nn), "d": z(2 * nn), "b": a(f"b{li + 1}", 2 * nn),
+                            "S": z(36 * nn), "dinv": z(4 * nn), "d": z(2 * nn), "b": a(f"b{li + 1}", 2 * nn),
                             "xa": a(f"xa{li + 1}", 2 * nn), "xb": a(f"xb{li + 1}", 2 * nn), "r": a(f"r{li + 1}", 2 * nn), "lmax": None})
         self.coarse_inv, self.desc, self.setup_seconds, self.lmax0 = None, None, None, None
         self._graph, self._graph_key = None, None
@@ -391,9 +392,21 @@ class MultigridPCG:
         self.setup_seconds = time.perf_counter() - t0
         return self
 
+    @staticmethod
+    def block_apply(dinv, v):
+        """D^-1 v for the two-plane block inverse ``dinv`` (planes A = (i00, i01), B = (i01, i11) per node)."""
+        n = v.numel()
+        a, b, v2 = dinv[:n].view(-1, 2), dinv[n:2 * n].view(-1, 2), v.view(-1, 2)
+        return torch.stack([a[:, 0] * v2[:, 0] + a[:, 1] * v2[:, 1], b[:, 0] * v2[:, 0] + b[:, 1] * v2[:, 1]], dim=1).reshape(-1)
+
+    def block_jacobi(self, k_vals, out=None):
+        out = self.minv if out is None else out
+        call("fem_mg_block_jacobi", self.plan._h, _ptr(k_vals), _ptr(self.mask), _ptr(out), _stream())
+        return out
+
     def _power_fine(self, k_vals, iters=20):
         P = self.plan
-        dinv = P.jacobi(k_vals, self.mask)
+        dinv = self.block_jacobi(k_vals)
         g = torch.Generator(device=self.device).manual_seed(11 + self.rank)
         v = torch.randn(P.n_dof, dtype=torch.float64, device=self.device, generator=g) * self.mask
         y = torch.empty_like(v)
@@ -402,7 +415,7 @@ class MultigridPCG:
             if self.part is not None:
                 self.part.halo_exchange(v)
             P.spmv(k_vals, v, mask=self.mask, out=y)
-            y *= dinv
+            y = self.block_apply(dinv, y)
             nrm = y.square().sum().reshape(1)
             self._all_reduce(nrm)
             lam = float(nrm.sqrt().item())
@@ -421,7 +434,7 @@ class MultigridPCG:
             if self.part is not None and not lv["rep"]:
                 self._halo_rows(lv, v.view(1, lv["nrows"], w))
             call("fem_mg_stencil_apply", lv["nxn"], lv["nrows"], lo, hi, _ptr(lv["S"]), _ptr(v), _ptr(y), _stream())
-            y *= lv["dinv"]
+            y = self.block_apply(lv["dinv"], y)
             nrm = y[lo * w:hi * w].square().sum().reshape(1)
             if not lv["rep"]:
                 self._all_reduce(nrm)
@@ -524,12 +537,12 @@ class MultigridPCG:
         k, L = self.degree, self.n_levels
         return 3 + (2 * k + 3) + (L - 1) * (2 * k + 3) + 1
 
-    def solve(self, k_vals, rhs, rtol=1e-10, maxit=500, check_every=5, iters=None):
+    def solve(self, k_vals, rhs, rtol=1e-10, maxit=500, check_every=2, iters=None):
         """Returns (x, iterations, relative residual).  ``iters``: run exactly that many iterations (benchmarks)."""
         if self.desc is None:
             self.setup(k_vals)
         P, s, n = self.plan, self.scal, self.plan.n_dof
-        P.jacobi(k_vals, self.mask, out=self.minv)
+        self.block_jacobi(k_vals)
         if self.k32 is not None:
             call("fem_mg_to_f32", P.nnz, _ptr(k_vals), _ptr(self.k32), _stream())
         call("fem_mg_pcg_init", n, _ptr(rhs), _ptr(self.mask), _ptr(self.r), _ptr(self.x), _ptr(s), _stream())

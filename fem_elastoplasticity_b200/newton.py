@@ -67,7 +67,7 @@ class NewtonSolver:
             if self._mg is None:
                 from .mg import MultigridPCG
                 self._mg = MultigridPCG(self.plan, self.mask, part=self.part, free_mask=self.free).setup(self.k_elast)
-            x, its, rel = self._mg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=min(self.pcg_maxit, 2000), check_every=min(self.check_every, 4))
+            x, its, rel = self._mg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=min(self.pcg_maxit, 2000), check_every=2)
             return x.clone(), its, rel
         if self._dpcg is not None:                        # ghost rows of the returned vector are current
             x, its = self._dpcg.solve(k_vals, rhs, rtol=self.pcg_rtol, maxit=self.pcg_maxit, check_every=self.check_every)

@@ -205,7 +205,7 @@ int fem_tl_apply(int64_t n_n, int mode, const double* r, const double* minv, con
  * Level 0 is the mesh itself (the CSR matrix of the plan); level l >= 1 is a grid of bilinear (Q1) cells of 2^l lattice
  * steps, stored as a 9-point stencil of 2x2 blocks, S[(4*slot + 2*i + j) * n + node], slot = 3*(dy+1) + (dx+1); the
  * operators are Galerkin products A_{l+1} = P^T A_l P with P = bilinear interpolation, Dirichlet DOFs masked on level 0.
- * Smoother: Chebyshev polynomial of `degree` in D^-1 A (point Jacobi), the same before and after the coarse correction,
+ * Smoother: Chebyshev polynomial of `degree` in D^-1 A (D = the nodes' 2x2 diagonal blocks), the same before and after the coarse correction,
  * so the V-cycle is a symmetric positive definite preconditioner for the CG of the Newton step
  * (replaces the dense LU of Plasticity2D_DP/pythonFEM.py:1062-1066; any SPD preconditioner gives the same solution).
  * Every transfer is a gather (no atomics): results are bit-reproducible run to run.
@@ -231,7 +231,7 @@ typedef struct fem_mg_level {
                                                            distributed level; its share of the rows on the first replicated level) */
   const double* S;                                      /* [36][nxn*nrows] */
   const float* S32;                                     /* optional FP32 copy of S streamed by the smoother / residual (NULL: use S) */
-  const double* dinv;                                   /* [2*nxn*nrows] */
+  const double* dinv;                                   /* [4*nxn*nrows]: inverse 2x2 diagonal blocks, plane A[node] = (i00, i01), plane B = (i01, i11) */
   double *b, *xa, *xb, *d, *r;                          /* work vectors, [2*nxn*nrows] */
   double c1[FEM_MG_MAX_DEGREE], c2[FEM_MG_MAX_DEGREE];  /* Chebyshev recurrence d = c1 d + c2 D^-1 r */
   fem_mg_exchange ex_xa, ex_xb, ex_r, ex_b;             /* ex_b: gather of b to every rank (first replicated level) */
@@ -243,7 +243,7 @@ typedef struct fem_mg_desc {
   const int32_t* node_lat;           /* [n_n] node -> lattice point iy_local*LX + ix */
   int64_t own_node_lo, own_node_hi;  /* nodes of the owned lattice rows (a contiguous id range); ghost nodes are never written */
   const uint8_t* mask;               /* unknowns of this rank on level 0 (free AND owned) */
-  const double* dinv;                /* level 0: masked inverse diagonal of the CURRENT matrix (fem_jacobi_setup) */
+  const double* dinv;                /* level 0: masked inverse 2x2 diagonal blocks of the CURRENT matrix (fem_mg_block_jacobi), [2*n_dof] in two planes */
   double *xa, *xb, *d, *r;           /* level 0 work vectors [n_dof] */
   double c1[FEM_MG_MAX_DEGREE], c2[FEM_MG_MAX_DEGREE];
   fem_mg_exchange ex_xa, ex_xb, ex_r;
@@ -263,6 +263,8 @@ int fem_mg_galerkin_fine(const fem_plan* plan, const double* K_vals, const uint8
 int fem_mg_galerkin_stencil(int nxf, int nrows_f, int g0f, int nrows_global_f, const double* Sf, int nxc, int nrows_c, int g0c,
                             int row_lo, int row_hi, double* Sc, fem_stream stream);
 int fem_mg_level_finalize(int64_t n, double* S, double thresh, double* dinv, fem_stream stream);
+/* dinv[2*n_dof]: inverse of every node's 2x2 diagonal block (block-Jacobi smoother), rows/columns of masked DOFs zero */
+int fem_mg_block_jacobi(const fem_plan* plan, const double* K_vals, const uint8_t* mask, double* dinv, fem_stream stream);
 int fem_mg_stencil_apply(int nxn, int nrows, int row_lo, int row_hi, const double* S, const double* x, double* y, fem_stream stream);
 int fem_mg_stencil_to_dense(int nxn, int nrows, const double* S, double* A, fem_stream stream);
 /* z = V(r): one V-cycle on the current matrix K_vals (level 0) and the stored coarse operators; if dot != NULL, *dot += r'z

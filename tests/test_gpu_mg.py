@@ -64,20 +64,24 @@ def test_hierarchy_and_vcycle_match_numpy_statement(fem, nx, ny):
         got = stencil_to_scipy(lv["S"].cpu().numpy(), lv["nxn"], lv["nrows"])
         want = ref.A[li + 1]
         assert abs(got - want).max() <= 1e-12 * abs(want).max(), li
-        d = want.diagonal()
-        np.testing.assert_allclose(lv["dinv"].cpu().numpy(), 1.0 / d, rtol=1e-12)
-    # eigenvalue bounds: power iteration underestimates, never above the true lambda_max by more than the 1.1 margin
+    # inverse 2x2 diagonal blocks (block-Jacobi smoother) and eigenvalue bounds: the power iteration underestimates, never
+    # above the true lambda_max by more than the 1.1 margin
     import scipy.sparse.linalg as spla
-    for l, lm in enumerate([M.lmax0] + [lv["lmax"] for lv in M.lv[:-1]]):
-        A = ref.A[l]
-        d = A.diagonal()
-        di = np.where(d != 0, 1.0 / np.where(d != 0, d, 1.0), 0.0)
-        true = spla.eigs(spla.LinearOperator(A.shape, matvec=lambda v: di * (A @ v)), k=1, which="LM", return_eigenvectors=False, tol=1e-6)[0].real
+    ref.set_bounds([1.0] * M.n_levels)
+    M.block_jacobi(k_el)
+    for l, (lm, dv) in enumerate([(M.lmax0, M.minv)] + [(lv["lmax"], lv["dinv"]) for lv in M.lv[:-1]]):
+        A, Di = ref.A[l], ref.dinv[l]
+        n = A.shape[0]
+        dv = dv.cpu().numpy()
+        got = np.stack([dv[0:n:2], dv[1:n:2], dv[n:2 * n:2], dv[n + 1:2 * n:2]])          # i00, i01, i10, i11 per node
+        want_b = np.stack([Di.diagonal()[0::2], Di.diagonal(1)[0::2], Di.diagonal(-1)[0::2], Di.diagonal()[1::2]])
+        np.testing.assert_allclose(got, want_b, rtol=1e-11, atol=1e-13 * np.abs(want_b).max())
+        true = spla.eigs(spla.LinearOperator(A.shape, matvec=lambda v: Di @ (A @ v)), k=1, which="LM", return_eigenvectors=False, tol=1e-6)[0].real
         assert 0.9 * true <= lm <= 1.12 * true, (l, lm, true)
     # one V-cycle on the tangent matrix (coarse operators of K_elast) against the NumPy statement
     ref.set_fine(Ktan)
     ref.set_bounds([M.lmax0] + [lv["lmax"] for lv in M.lv[:-1]])
-    P.jacobi(k_tan, mask, out=M.minv)
+    M.block_jacobi(k_tan)
     rng = np.random.default_rng(3)
     rv = rng.standard_normal(P.n_dof) * q
     z = torch.zeros(P.n_dof, dtype=torch.float64, device="cuda")
@@ -157,7 +161,7 @@ def test_fine_step_code_paths_agree(fem):
     b, x = rnd(), rnd()
     for f32 in (False, True):
         M = mg.MultigridPCG(P, mask, smoother_f32=f32).setup(k)
-        P.jacobi(k, mask, out=M.minv)
+        M.block_jacobi(k)
         if f32:
             _lib.call("fem_mg_to_f32", P.nnz, fem["plan"]._ptr(k), fem["plan"]._ptr(M.k32), fem["plan"]._stream())
         d0 = rnd()
@@ -177,7 +181,7 @@ def test_fine_step_code_paths_agree(fem):
                 assert float((a - c).abs().max()) <= 1e-12 * float(c.abs().max())
             assert abs(outs[0][3] - o[3]) <= 1e-11 * abs(o[3])
         r_ref = (b - P.spmv(k, x)) * mask
-        d_ref = M.desc.c1[1] * d0 + M.desc.c2[1] * M.minv * r_ref
+        d_ref = M.desc.c1[1] * d0 + M.desc.c2[1] * M.block_apply(M.minv, r_ref)
         tol = 1e-12 if not f32 else 1e-6
         assert float((outs[0][2] - r_ref).abs().max()) <= tol * float(r_ref.abs().max())
         assert float((outs[0][1] - d_ref).abs().max()) <= tol * float(d_ref.abs().max())
