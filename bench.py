@@ -561,15 +561,15 @@ def run_gpu(args):
         # node pointers, x once, y once, mask; Jacobi-PCG vector kernels: 10 vector passes) - ncu agrees within 4 % (profiles/r2c)
         "spmv_own": 8.5 * nnz_rank + (4.0 + 16.0 + 16.0 + 2.0) * P.n_n,
         "pcg_iter_own": 8.5 * nnz_rank + 38.0 * P.n_n + 80.0 * n_dof_rank,
-        # level-0 multigrid step: FP32 values (4 B/nnz) + block positions + node pointers + b, D^-1, d, x in, d, x out
-        "mg_cheb": (4.5 if (mgs is not None and mgs.k32 is not None) else 8.5) * nnz_rank + 4.0 * P.n_n + 48.0 * n_dof_rank,
+        # level-0 multigrid step: FP32 values (4 B/nnz) + block positions + node pointers + b, D^-1 (2x2 blocks), d, x in, d, x out
+        "mg_cheb": (4.5 if (mgs is not None and mgs.k32 is not None) else 8.5) * nnz_rank + 4.0 * P.n_n + 56.0 * n_dof_rank,
         "mg_resid": (4.5 if (mgs is not None and mgs.k32 is not None) else 8.5) * nnz_rank + 6.0 * P.n_n + 24.0 * n_dof_rank,
     }
     pcg_ms_iter = t_jac / max(args.pcg_iters, 1)
     conv = None
     if mgs is not None:
         its = int(solve_info["iterations"])
-        conv = {"preconditioner": f"geometric multigrid V-cycle: {mgs.n_levels + 1} levels, Chebyshev-Jacobi smoother degree {mgs.degree} (interval lambda_max/{mgs.ratio:g}), "
+        conv = {"preconditioner": f"geometric multigrid V-cycle: {mgs.n_levels + 1} levels, Chebyshev smoother of degree {mgs.degree} on block Jacobi (2x2 node blocks; interval lambda_max/{mgs.ratio:g}), "
                                   f"Galerkin coarse operators of K_elast, dense solve on {2 * mgs.lv[-1]['n']} DOFs",
                 "converged": True, "rtol": args.rtol, "iterations": its, "relres": solve_info["relres"], "true_relres": true_rel,
                 "seconds": t_pcg * 1e-3, "ms_per_iteration": t_pcg / max(its, 1), "setup_seconds": mgs.setup_seconds,

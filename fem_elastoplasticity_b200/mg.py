@@ -132,7 +132,7 @@ class MultigridPCG:
     always uses the matrix being solved.  ``solve`` mirrors TwoLevelPCG.solve."""
 
     def __init__(self, plan, mask, part=None, free_mask=None, degree=2, ratio=16.0, max_coarse_dofs=2500, lattice=None, use_graph=True,
-                 smoother_f32=True):
+                 smoother_f32=True, replicate_below=50000):
         check_abi()
         self.plan, self.mask = plan, mask
         self.part = part if (part is not None and part.world > 1) else None
@@ -175,7 +175,7 @@ class MultigridPCG:
             if not bool((self.node_lat == torch.arange(plan.n_n, dtype=torch.int32, device=dev)).all()):
                 raise MultigridUnsupported("partitioned multigrid needs lattice-ordered node numbering")
         self.own_nodes = (own_rows[0] * LX, own_rows[1] * LX) if self.part is not None else (0, plan.n_n)
-        self.layouts = level_layouts(LX, NY, owned, max_coarse_dofs=max_coarse_dofs)
+        self.layouts = level_layouts(LX, NY, owned, max_coarse_dofs=max_coarse_dofs, replicate_below=replicate_below)
         self.n_levels = len(self.layouts)
         # ---- buffers (on a partition the vectors whose ghost rows travel live in one symmetric-memory arena)
         self._arena_slots, self._ex_ids = {}, {}

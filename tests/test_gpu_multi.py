@@ -207,7 +207,8 @@ def _mg_worker(rank, world, port, nx, ny, out_dir):
     b_global = np.random.default_rng(9).standard_normal(2 * (nx + 1) * (ny + 1))
     lo = part.iy0 * part.row_dofs
     rhs = torch.as_tensor(b_global[lo:lo + P.n_dof].copy()).to(dev)
-    M = MultigridPCG(P, mask, part=part, free_mask=P.mask_u8(mesh["Q"]), max_coarse_dofs=300).setup(k_el)
+    # replicate_below=0: keep the small levels of this test mesh distributed (ghost-row exchanges on every level but the last)
+    M = MultigridPCG(P, mask, part=part, free_mask=P.mask_u8(mesh["Q"]), max_coarse_dofs=300, replicate_below=0).setup(k_el)
     res = {"levels": np.array([[lv["rep"], lv["first_rep"]] for lv in M.lv])}
     for tag, graph in (("graph", True), ("eager", False)):
         M.use_graph = graph
@@ -258,7 +259,7 @@ def test_multi_gpu_multigrid_matches_single_gpu(tmp_path):
             got[lo + a:lo + e] = d[tag][a:e]
         assert not np.isnan(got).any()
         np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
-        assert abs(int(d0[tag + "_its"]) - its1) <= 1, (tag, int(d0[tag + "_its"]), its1)
+        assert abs(int(d0[tag + "_its"]) - its1) <= 2, (tag, int(d0[tag + "_its"]), its1)
     print(f"multigrid PCG iterations: {world} GPUs", int(d0["graph_its"]), "1 GPU", its1)
 
 
