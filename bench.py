@@ -358,10 +358,14 @@ def run_gpu(args):
     from fem_elastoplasticity_b200.plan import axpby
     # the step's linear solve: CG preconditioned by a geometric multigrid V-cycle, driven to rtol (coarse operators of K_elast,
     # built once per mesh as in the Newton loop); --solver jacobi restores round 1's fixed number of Jacobi iterations
-    mgs = None
+    mgs, solver_note = None, None
     if args.solver == "multigrid":
         from fem_elastoplasticity_b200.mg import MultigridPCG
-        mgs = MultigridPCG(P, mask, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio).setup(k_el)
+        try:
+            mgs = MultigridPCG(P, mask, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio).setup(k_el)
+        except Exception as e:  # noqa: BLE001  (e.g. no symmetric memory on this box: every rank fails at the same collective)
+            mgs, solver_note = None, f"multigrid unavailable ({type(e).__name__}: {e}); step timed with {args.pcg_iters} fixed Jacobi-PCG iterations"
+            print(solver_note, file=sys.stderr)
     solve_info = {}
 
     def ev():
@@ -644,7 +648,7 @@ def run_gpu(args):
         "e2e": {"value": n_e_tot / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "h2d_bytes_per_step": int(72 * P.n_int),
                 "d2h_bytes_per_step": int(8 * P.nnz), "what": "FemPlan.assemble_tangent: pinned host DS -> device -> kernel -> pinned host K values, every step; two steps in flight "
                         "(double-buffered, H2D of step i+1 overlaps D2H of step i)", "steps": e2e_steps},
-        "e2e_step": facade, "host_numa_binding": numa,
+        "e2e_step": facade, "host_numa_binding": numa, "solver_note": solver_note,
         "gpu_launches": int(launches["n"] * args.steps),
     }
     if world == 1 and not args.no_cpu_baseline:
