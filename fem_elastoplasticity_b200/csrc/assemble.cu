@@ -34,9 +34,12 @@ struct AsmArgs {
   int boxw;
   unsigned long long* slice_counter;  // dynamic tile scheduler of the persistent kernels (zeroed before launch)
   int acc_rows;         // 4 * max_degree
+  int canon;            // 1: slices of the reference's regular triangulation take the straight-line path of variant D
   double dev2[9];       // 2*Dev (column-major) formed as numpy forms it (:579-582)
   double vol[9];
 };
+
+__device__ __forceinline__ bool g_canon_enabled(const AsmArgs& A) { return A.canon != 0; }
 
 constexpr int ACC_LD = 33;  // padded leading dimension: bank = (entry + lane) mod 16 for doubles
 
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A,
   const int bw = A.boxw;
   unsigned char* wbase = smem_raw + (size_t)warp * L::warp_b(bw);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase + 2 * L::box_b(bw));
-  const int n_box = A.stage_box[slice * 3];
+  const int n_box = A.stage_box[slice * 3] & 0xFF;
   const bool staged = n_box >= 1 && n_box <= 2;  // warp-uniform
   if (staged) {
     if (lane == 0) {
@@ -484,6 +487,12 @@ __global__ void __launch_bounds__(128) assemble_rows_tma_kernel(const AsmArgs A,
     }
 }
 
+#ifndef FEM_ASM_CHUNK
+#define FEM_ASM_CHUNK 2  // consecutive slices per claim of the dynamic scheduler of variant D (measured: 1: see NC, 2: 0.922 ms, 4: 0.942, 8: 0.992, 16: 1.176)
+#endif
+#ifndef FEM_ASM_NC
+#define FEM_ASM_NC 1     // interleaved claim counters of variant D (1, 2, 4: no difference once claims come in chunks of two)
+#endif
 #ifndef FEM_ASM_UNROLL
 #define FEM_ASM_UNROLL 2  // incidence steps per rotation of the register queue in variant D (1, 2, 4 or 8)
 #endif
@@ -522,6 +531,62 @@ __device__ __forceinline__ void issue_box(const StageMaps& M, unsigned char* bb,
   if (FORCE) tma_box_2d(smem_u32(bb), &M.s, start, bar);
 }
 
+// ---- fast path of variant D for the reference's regular triangulation --------------------------------------------------
+// On the uniform P1 meshes of the reference's generator (get_nodes_1, Plasticity2D_DP/pythonFEM.py:73-122: cells split along
+// V2-V4, two triangles per cell, node id = ix + iy (nx + 1)) every interior node meets the same six elements in the same
+// roles: its local index in each element and the positions of the element's three nodes in its sorted neighbour list are
+// CONSTANTS (derived with the oracle's mesh; common.cuh).  A slice whose 32 incidence lists all carry exactly that pattern -
+// flagged by the plan (build_stage: a warp vote on the incidence words); ~97 % of the slices of config 4 - is processed
+// by straight-line code on lane 0's incidence words (the others' staged positions are two elements further per lane): no queue,
+// no validity tests, no selects on the local node, and the accumulators addressed statically instead of through a
+// `switch` on the slot.  Same incidences in the same order with the same arithmetic: bit-identical to the generic path
+// (test_assembly_variants_agree_bitwise), which every other slice and every other mesh still takes.
+template <int MODE, bool FORCE, int K, int MAXDEG>
+__device__ __forceinline__ void canon_incidence(const AsmArgs& A, const unsigned char* box, const int o, const int bw, double (&acc)[MAXDEG][4],
+                                                double& f0, double& f1) {
+  using L = StageLayout<MODE, FORCE>;
+  static_assert(MAXDEG >= 7, "the canonical node has seven neighbours");
+  PointData<3, MODE, FORCE> pd;
+  const double* g = reinterpret_cast<const double*>(box) + o;
+  pd.w = g[0];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    pd.d1[p] = g[(1 + p) * bw];
+    pd.d2[p] = g[(4 + p) * bw];
+  }
+  const unsigned char* bb = box + L::geom_b(bw);
+  const double* t0 = reinterpret_cast<const double*>(bb) + o;
+  if (MODE == MODE_ELASTIC) {
+    pd.raw[0] = t0[0];
+    pd.raw[1] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pd.raw[k] = t0[k * bw];
+    if (MODE == MODE_TANGENT_REF) {
+      pd.raw[MODE == MODE_TANGENT_REF ? 9 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw)) + o)[0];
+      pd.raw[MODE == MODE_TANGENT_REF ? 10 : 0] = (reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw)) + o)[0];
+    }
+  }
+  if (FORCE) {
+    const double* sp = reinterpret_cast<const double*>(bb + L::t0_b(bw) + L::t1_b(bw) + L::t2_b(bw)) + o;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pd.s[k] = sp[k * bw];
+  }
+  double tx[3], ty[3];
+  point_terms<3, MODE, FORCE>(A, pd, canon_la(K), tx, ty, f0, f1);
+#pragma unroll
+  for (int lb = 0; lb < 3; ++lb) {
+    const int slot = canon_slot(K, lb);  // compile-time after unrolling
+    const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+    const double p00 = tx[0] * b1, p01 = tx[2] * b2, p10 = tx[1] * b2, p11 = tx[2] * b1;
+    const double p20 = ty[0] * b1, p21 = ty[2] * b2, p30 = ty[1] * b2, p31 = ty[2] * b1;
+    acc[slot][0] = (acc[slot][0] + p00) + p01;
+    acc[slot][1] = (acc[slot][1] + p10) + p11;
+    acc[slot][2] = (acc[slot][2] + p20) + p21;
+    acc[slot][3] = (acc[slot][3] + p30) + p31;
+  }
+}
+
 template <int MODE, bool FORCE, int MAXDEG, int BW>
 __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A, const __grid_constant__ StageMaps M) {
   constexpr int NP = 3;
@@ -545,10 +610,31 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
   // is a window that slides smoothly through the mesh.  (A static warp + k*n_warps assignment advances in lock-step
   // rounds: the two node rows that share a row of elements then fetch it at the same instant and both miss in L2 -
   // measured 1.5x DRAM reads.)  The claim for slice s+2 is made while slice s is being computed.
-  auto claim = [&]() -> int64_t {
-    unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(A.slice_counter, 1ULL);
-    return (int64_t)__shfl_sync(0xffffffffu, v, 0);
+  // The counter is claimed in CHUNKS of consecutive slices: one atomic per slice on a single address is a serial resource
+  // (250 000 claims in 1 ms = the kernel's run time; the broadcast of the claimed value was 25 % of all stall samples,
+  // profiles/r2w).  A warp owns two chunks at any time; the atomic for the chunk after the current one is issued when the
+  // current chunk starts and its value is only read (shuffled from lane 0) one whole chunk later.
+  // The chunks are dealt from FEM_ASM_NC interleaved counters (counter j hands out the chunks c = NC k + j to the CTAs with
+  // blockIdx % NC == j): the counters advance at the same pace, so the set of slices in flight is still a window sliding
+  // through the mesh, at 1/NC of the atomic rate per address.
+  constexpr int CHUNK = FEM_ASM_CHUNK, NC = FEM_ASM_NC;
+  unsigned long long pending = 0;  // lane 0: chunk index returned by the atomic in flight
+  const int cj = (int)(blockIdx.x % NC);
+  auto request = [&]() {
+    if (lane == 0) pending = atomicAdd(A.slice_counter + cj, 1ULL) * NC + cj;
+  };
+  auto collect = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, pending, 0) * CHUNK; };
+  request();
+  int64_t cbase = collect();
+  request();
+  int cpos = 0;
+  auto claim = [&]() -> int64_t {  // next slice of this warp's sequence
+    if (cpos == CHUNK) {
+      cbase = collect();
+      request();
+      cpos = 0;
+    }
+    return cbase + cpos++;
   };
   int64_t slice = claim();
   int64_t slice1 = claim();  // the slice after the current one
@@ -556,10 +642,13 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
   constexpr int CH = 8;  // plan guarantees <= 8 incidences per node when stage_ok
   // Per-slice bookkeeping, fetched one slice ahead (two for the SELL offsets the incidence words depend on):
   //   box table {nb, st0, st1}, node degree/base, SELL offset + width, incidence words.
-  struct Book { int nb, st0, st1, deg, width; int64_t base, sbase; };
+  struct Book { int nb, cn, st0, st1, deg, width; int64_t base, sbase; };
   auto load_box = [&](int64_t s, Book& k) {
-    k.nb = 0; k.st0 = 0; k.st1 = 0;
-    if (s < n_slices) { k.nb = A.stage_box[s * 3]; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2]; }
+    k.nb = 0; k.cn = 0; k.st0 = 0; k.st1 = 0;
+    if (s < n_slices) {
+      const int raw = A.stage_box[s * 3];  // boxes | canonical flag << 8
+      k.nb = raw & 0xFF; k.cn = (raw >> 8) & 1; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2];
+    }
   };
   auto load_node = [&](int64_t s, Book& k) {
     k.deg = 0; k.base = 0;
@@ -576,10 +665,19 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
   };
   Book cur, nxt;
   uint32_t words[CH], nwords[CH];
+  // incidence words of a slice: canonical slices (flag from the plan) read lane 0's words - one sector per word instead of
+  // four - and derive the staged positions (two elements further per lane)
+  auto load_words = [&](const Book& k, uint32_t (&w)[CH]) {
+    const bool cn = k.cn != 0 && A.canon != 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      w[i] = (i < k.width) ? __ldcs(A.inc_stage + k.sbase + (int64_t)i * 32 + (cn ? 0 : lane)) : 0u;
+      if (cn && i < 6) w[i] += 2u * (uint32_t)lane;
+    }
+  };
   load_box(slice, cur); load_node(slice, cur); load_sell(slice, cur);
   load_sell(slice1, nxt);
-#pragma unroll
-  for (int i = 0; i < CH; ++i) words[i] = (i < cur.width) ? __ldcs(A.inc_stage + cur.sbase + (int64_t)i * 32 + lane) : 0u;
+  load_words(cur, words);
   if (slice < n_slices && lane == 0 && cur.nb >= 1 && cur.nb <= 2) {
     issue_box<MODE, FORCE>(M, box0, bw, cur.st0, bar0);
     if (cur.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, cur.st1, bar1);
@@ -590,8 +688,7 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
     // requests for the next slice (and the SELL offsets of the one after) fly during this slice's computation
     load_box(next, nxt);
     load_node(next, nxt);
-#pragma unroll
-    for (int i = 0; i < CH; ++i) nwords[i] = (i < nxt.width) ? __ldcs(A.inc_stage + nxt.sbase + (int64_t)i * 32 + lane) : 0u;
+    load_words(nxt, nwords);
     Book nn;
     load_sell(slice2, nn);
     const int nb = cur.nb;
@@ -601,6 +698,23 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
 #pragma unroll
     for (int j = 0; j < MAXDEG; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
     double f0 = 0.0, f1 = 0.0;
+        const bool canon = MAXDEG >= 7 && nb == 2 && cur.cn != 0 && g_canon_enabled(A);  // flag set by build_stage (plan.cu)
+    if (canon) {
+      mbar_wait(bar0, ph0);
+      ph0 ^= 1;
+      canon_incidence<MODE, FORCE, 0, MAXDEG>(A, box0, (int)(words[0] & 0x1FF), bw, acc, f0, f1);
+      canon_incidence<MODE, FORCE, 1, MAXDEG>(A, box0, (int)(words[1] & 0x1FF), bw, acc, f0, f1);
+      canon_incidence<MODE, FORCE, 2, MAXDEG>(A, box0, (int)(words[2] & 0x1FF), bw, acc, f0, f1);
+      __syncwarp();
+      if (lane == 0 && nxt.nb >= 1 && nxt.nb <= 2) issue_box<MODE, FORCE>(M, box0, bw, nxt.st0, bar0);
+      mbar_wait(bar1, ph1);
+      ph1 ^= 1;
+      canon_incidence<MODE, FORCE, 3, MAXDEG>(A, box1, (int)(words[3] & 0x1FF) - bw, bw, acc, f0, f1);
+      canon_incidence<MODE, FORCE, 4, MAXDEG>(A, box1, (int)(words[4] & 0x1FF) - bw, bw, acc, f0, f1);
+      canon_incidence<MODE, FORCE, 5, MAXDEG>(A, box1, (int)(words[5] & 0x1FF) - bw, bw, acc, f0, f1);
+      __syncwarp();
+      if (lane == 0 && nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
+    } else
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       // pass 0: incidences whose element lives in box 0 (or every incidence on the direct-load path); pass 1: box 1.
@@ -722,7 +836,7 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
     }
     slice = next;
     slice1 = slice2;
-    cur.nb = nxt.nb; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
+    cur.nb = nxt.nb; cur.cn = nxt.cn; cur.st0 = nxt.st0; cur.st1 = nxt.st1; cur.deg = nxt.deg; cur.base = nxt.base;
     cur.sbase = nxt.sbase; cur.width = nxt.width;
     nxt.sbase = nn.sbase; nxt.width = nn.width;
 #pragma unroll
@@ -772,10 +886,13 @@ __global__ void __launch_bounds__(256) assemble_rows_ps_kernel(const AsmArgs A, 
   int64_t slice1 = claim();
   uint32_t ph0 = 0, ph1 = 0;
   constexpr int CH = 8;
-  struct Book { int nb, st0, st1, deg, width; int64_t base, sbase; };
+  struct Book { int nb, cn, st0, st1, deg, width; int64_t base, sbase; };
   auto load_box = [&](int64_t s, Book& k) {
-    k.nb = 0; k.st0 = 0; k.st1 = 0;
-    if (s < n_slices) { k.nb = A.stage_box[s * 3]; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2]; }
+    k.nb = 0; k.cn = 0; k.st0 = 0; k.st1 = 0;
+    if (s < n_slices) {
+      const int raw = A.stage_box[s * 3];  // boxes | canonical flag << 8
+      k.nb = raw & 0xFF; k.cn = (raw >> 8) & 1; k.st0 = A.stage_box[s * 3 + 1]; k.st1 = A.stage_box[s * 3 + 2];
+    }
   };
   auto load_node = [&](int64_t s, Book& k) {
     k.deg = 0; k.base = 0;
@@ -941,7 +1058,7 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   int warps = 4;
   size_t smem = (size_t)warps * L::warp_b(bw);
   if (smem > 227 * 1024) return -1;
-  if (g_fem_tuning.assemble_variant == 7 || (g_fem_tuning.assemble_variant == 0 && MODE == MODE_ELASTIC)) {  // one slice per warp
+  if (g_fem_tuning.assemble_variant == 7) {  // one slice per warp (C); the default is D for every mode: 0.740 vs 0.831 ms for K_elast
     auto kern = assemble_rows_tma_kernel<MODE, FORCE, 8>;
     FEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)fem_div_up(P->n_slices, warps), warps * 32, smem, st>>>(A, M);
@@ -970,9 +1087,11 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
     if (blocks > need) blocks = need;
     // one of FEM_SLICE_COUNTERS counters of this plan, round-robin per launch (atomic: host threads may launch concurrently),
     // so up to FEM_SLICE_COUNTERS launches of one plan may be in flight on different streams without sharing a counter
+    // (variant D spreads its claims over FEM_ASM_NC interleaved counters: a group of FEM_ASM_NC consecutive ones)
     static std::atomic<unsigned> launch_no{0};
-    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8) + (launch_no.fetch_add(1u) % FEM_SLICE_COUNTERS);
-    FEM_CUDA_CHECK(cudaMemsetAsync(A.slice_counter, 0, sizeof(unsigned long long), st));
+    static_assert(FEM_SLICE_COUNTERS % FEM_ASM_NC == 0, "counter groups");
+    A.slice_counter = reinterpret_cast<unsigned long long*>(P->dscratch + 8) + FEM_ASM_NC * (launch_no.fetch_add(1u) % (FEM_SLICE_COUNTERS / FEM_ASM_NC));
+    FEM_CUDA_CHECK(cudaMemsetAsync(A.slice_counter, 0, FEM_ASM_NC * sizeof(unsigned long long), st));
     kern<<<(unsigned)blocks, warps * 32, smem, st>>>(A, M);
   }
   FEM_CUDA_CHECK(cudaGetLastError());
@@ -1075,6 +1194,7 @@ static void fill_args(const fem_plan* P, AsmArgs& A) {
   A.nbr_ptr = P->nbr_ptr; A.slice_ptr = P->slice_ptr; A.inc_key = P->inc_key; A.inc_meta = P->inc_meta;
   A.dphi1 = P->dphi1; A.dphi2 = P->dphi2; A.weight = P->weight;
   elastic_coeffs(A.dev2, A.vol);
+  A.canon = g_fem_tuning.assemble_canon != 2;  // tuning key assemble_canon = 2 switches the regular-triangulation fast path off
 }
 
 extern "C" int fem_assemble_elastic(const fem_plan* P, const double* shear, const double* bulk, double* K_vals,

@@ -35,6 +35,7 @@ struct FemTuning {
   int spmv_unroll;         // nodes per lane group in flight (0 = default)
   int spmv_staged;         // 0 auto (every operand streamed through shared memory when the tiles fit, else as 2), 1 gather x from global memory (round-1 kernel), 2 x staged, matrix through registers
   int peer_timeout_ms;     // bound of the in-kernel waits of the fused multi-GPU PCG (0 = 10 000 ms)
+  int assemble_canon;      // 0 auto (straight-line path for slices of the reference's regular triangulation), 2 off
   int strain_variant;      // 0/1 stored gradients (default), 2 P1 gradients recomputed from the coordinates (slower: L2 gathers)
   int peer_nowait;         // DIAGNOSTIC ONLY: fused multi-GPU PCG kernels skip their waits (wrong results; isolates the wait time)
 };
@@ -108,6 +109,24 @@ struct fem_plan {
   int tile_max_blocks;  // most 2x2 blocks in one tile (the streaming SpMV needs them to fit a shared-memory stage)
   int64_t bytes;
 };
+
+// ---- the regular triangulation of the reference's mesh generator (get_nodes_1, Plasticity2D_DP/pythonFEM.py:73-122) -------
+// incidence k = 0..5 (ascending element id): local index of the node, and slots of the element's nodes 0, 1, 2 packed 4 bits each
+//   k:      0        1        2        3        4        5
+//   la:     1        2        2        1        0        0
+//   slots: {0,3,2}  {0,1,3}  {1,4,3}  {2,3,5}  {3,6,5}  {3,4,6}
+__host__ __device__ constexpr int canon_la(int k) { return (0x001221 >> (4 * k)) & 15; }
+__host__ __device__ constexpr int canon_slot(int k, int lb) {
+  return ((k == 0 ? 0x230 : k == 1 ? 0x310 : k == 2 ? 0x341 : k == 3 ? 0x532 : k == 4 ? 0x563 : 0x643) >> (4 * lb)) & 15;
+}
+constexpr uint32_t CANON_MASK = 0x807FFE00u;  // valid bit, la, the three slots (everything but the staged position)
+__host__ __device__ constexpr uint32_t canon_word(int k) {
+  return 0x80000000u | ((uint32_t)canon_la(k) << 9) | ((uint32_t)canon_slot(k, 0) << 11) | ((uint32_t)canon_slot(k, 1) << 15) |
+         ((uint32_t)canon_slot(k, 2) << 19);
+}
+static_assert(canon_word(0) == 0x80118200u && canon_word(1) == 0x80188400u && canon_word(2) == 0x801a0c00u && canon_word(3) == 0x80299200u &&
+                  canon_word(4) == 0x802b1800u && canon_word(5) == 0x80321800u, "canonical incidence words (oracle mesh)");
+
 
 static inline int fem_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

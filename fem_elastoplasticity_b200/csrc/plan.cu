@@ -32,6 +32,7 @@ extern "C" int fem_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "peer_timeout_ms")) g_fem_tuning.peer_timeout_ms = value;
   else if (!strcmp(key, "peer_nowait")) g_fem_tuning.peer_nowait = value;
   else if (!strcmp(key, "strain_variant")) g_fem_tuning.strain_variant = value;
+  else if (!strcmp(key, "assemble_canon")) g_fem_tuning.assemble_canon = value;
   else {
     fem_set_error("unknown tuning key %s", key);
     return FEM_ERR_INVALID_ARG;
@@ -425,6 +426,9 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int bo
     for (int r = 0; r < nr && b < 2; ++r)
       for (int st = rs[r]; st < re[r] && b < 2; st += boxw) out[1 + b++] = st;
   }
+  // canonical slice (common.cuh): all 32 lists carry the interior-node pattern of the regular triangulation, incidences 0-2 in
+  // box 0 and 3-5 in box 1, staged positions advancing by two elements per lane: the assembly then needs lane 0's words only
+  bool canon_ok = nb == 2 && width >= 6 && slice * 32 + lane < n_n;
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     if (i >= width) break;
@@ -443,7 +447,12 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int bo
              (((meta >> 24) & 15u) << 19) | 0x80000000u;
     }
     inc_stage[at] = word;
+    const int li0 = __shfl_sync(0xffffffffu, (int)(word & 0x1FF), 0);
+    if (i < 6) canon_ok = canon_ok && (word & CANON_MASK) == canon_word(i) && (((int)(word & 0x1FF) >= boxw) == (i >= 3)) &&
+                          (int)(word & 0x1FF) == li0 + 2 * lane;
+    else canon_ok = canon_ok && word == 0u;
   }
+  if (__all_sync(0xffffffffu, canon_ok) && lane == 0) out[0] = nb | 0x100;
 }
 
 

@@ -311,7 +311,7 @@ int fem_vector_volume(const fem_plan* plan, const double* f_int, const double* h
 int fem_segment_sum_ordered(int64_t n_seg, const int64_t* seg_ptr, const double* vals, double* out, fem_stream stream);
 
 /* launch-shape knobs for benchmarking ("return_map_variant", "assemble_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm",
- * "spmv_staged", "peer_timeout_ms", "strain_variant");
+ * "spmv_staged", "peer_timeout_ms", "strain_variant", "assemble_canon");
  * value 0 restores the default.  Results never depend on them.                                     */
 int fem_set_tuning(const char* key, int value);
 
