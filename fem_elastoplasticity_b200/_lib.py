@@ -84,6 +84,9 @@ SIGNATURES = {
     "fem_transform": [_vp, _vp, _vp, _vp],
     "fem_vector_volume": [_vp, _vp, C.POINTER(_dbl), _vp, _vp],
     "fem_segment_sum_ordered": [_i64, _vp, _vp, _vp, _vp],
+    "fem_midpoints_p2_count": [_i64, _i64, _vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32), _vp],
+    "fem_midpoints_p2_fill": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "fem_midpoints_p2_destroy": [_vp, _vp],
     "fem_set_tuning": [C.c_char_p, _i32],
 }
 _RESTYPE = {"fem_last_error_string": C.c_char_p, "fem_plan_bytes": _i64}

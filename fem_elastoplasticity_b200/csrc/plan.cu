@@ -142,6 +142,9 @@ static int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaSt
   FEM_CUDA_CHECK(e);
   return FEM_OK;
 }
+int fem_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, cudaStream_t st) {  // midpoints.cu
+  return exclusive_scan_i32(in, out, n, st);
+}
 
 // ------------------------------------------------------------------------------------------------
 // incidence lists

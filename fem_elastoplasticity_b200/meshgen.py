@@ -102,7 +102,12 @@ def create_midpoints_p2(coord, elem):
     first vertex, midpoint) per boundary edge, coord_ext, elem_ext (6, n_e), elem_ed (3, n_e) midpoint index per element
     edge, edge_el (2, 2*n_e) the elements on either side of each midpoint (0 where the reference leaves its zeros).
     The reference finds the neighbour's edge slot from the position of one shared vertex, which presumes that the two
-    triangles traverse the edge in opposite directions; a mesh where they do not is rejected here."""
+    triangles traverse the edge in opposite directions; a mesh where they do not is rejected here.
+
+    CUDA tensors take the hand-written kernels (csrc/midpoints.cu: hash table of the edge keys + prefix sums, no sort); the
+    torch formulation below is the host-side statement of the same rule (CPU tensors only)."""
+    if coord.is_cuda:
+        return _create_midpoints_p2_cuda(coord, elem)
     elem = elem.to(torch.int64)
     dev = elem.device
     n_e, n_n = elem.shape[1], coord.shape[1]
@@ -133,3 +138,36 @@ def create_midpoints_p2(coord, elem):
     surf = torch.stack([fb[bnd], fa[bnd], mids]).to(torch.float64)
     return {"coord_mid": coord_mid, "surf": surf, "coord_ext": torch.cat([coord, coord_mid], dim=1),
             "elem_ext": torch.cat([elem, ind + n_n], dim=0), "elem_ed": ind.to(torch.float64), "edge_el": edge_el}
+
+
+def _create_midpoints_p2_cuda(coord, elem):
+    """create_midpoints_p2 through fem_midpoints_p2_count / _fill (include/fem_b200.h)."""
+    import ctypes as C
+    from ._lib import call
+    from .plan import _ptr, _stream
+    dev = coord.device
+    n_n, n_e = coord.shape[1], elem.shape[1]
+    coord = coord.to(torch.float64).contiguous()
+    e32 = elem.to(device=dev, dtype=torch.int32).contiguous()
+    handle, n_mid, n_bnd, status = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int()
+    with torch.cuda.device(dev):
+        call("fem_midpoints_p2_count", n_n, n_e, _ptr(e32), C.byref(handle), C.byref(n_mid), C.byref(n_bnd), C.byref(status), _stream())
+        try:
+            if status.value & 1:
+                raise ValueError("an edge is shared by more than two triangles")
+            if status.value & 2:
+                raise ValueError("inconsistently oriented triangles: the reference's neighbour-slot rule is undefined")
+            n_mid, n_bnd = n_mid.value, n_bnd.value
+            coord_mid = torch.empty((2, n_mid), dtype=torch.float64, device=dev)
+            ind = torch.empty((3, n_e), dtype=torch.int32, device=dev)
+            edge_el32 = torch.empty((2, n_mid), dtype=torch.int32, device=dev)
+            surf32 = torch.empty((3, n_bnd), dtype=torch.int32, device=dev)
+            call("fem_midpoints_p2_fill", handle, _ptr(coord), _ptr(coord_mid), _ptr(ind), _ptr(edge_el32), _ptr(surf32), _stream())
+        finally:
+            call("fem_midpoints_p2_destroy", handle, _stream())
+    ind = ind.to(torch.int64)
+    edge_el = torch.zeros((2, max(2 * n_e, n_mid)), dtype=torch.float64, device=dev)
+    edge_el[:, :n_mid] = edge_el32.to(torch.float64)
+    return {"coord_mid": coord_mid, "surf": surf32.to(torch.float64), "coord_ext": torch.cat([coord, coord_mid], dim=1),
+            "elem_ext": torch.cat([elem.to(device=dev, dtype=torch.int64), ind + n_n], dim=0), "elem_ed": ind.to(torch.float64),
+            "edge_el": edge_el}

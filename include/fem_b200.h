@@ -310,6 +310,24 @@ int fem_transform(const fem_plan* plan, const double* q_int, double* q_node, fem
 int fem_vector_volume(const fem_plan* plan, const double* f_int, const double* h_hatp, double* out, fem_stream stream);
 int fem_segment_sum_ordered(int64_t n_seg, const int64_t* seg_ptr, const double* vals, double* out, fem_stream stream);
 
+/* P1 -> P2 midpoint enrichment (create_midpoints_P2, tsx-tunnel/pythonFEM.py:1508-1626) without the reference's O(n_e^2)
+ * search: edge occurrences o = 3*element + edge (edges V2-V3, V3-V1, V1-V2) go into a device hash table keyed by the vertex
+ * pair; a midpoint's index is the number of edges whose first occurrence precedes its own (prefix sum) - the reference's
+ * visiting order, bit-identical numbering and coordinates.  Two calls because the output sizes are results:
+ * fem_midpoints_p2_count: elem [3][n_e] int32 (0-based, DEVICE, must stay alive until _fill) -> opaque handle, n_mid, n_bnd
+ *   (boundary edges) and status (bit 0: an edge is shared by more than two triangles; bit 1: two triangles traverse a shared
+ *   edge in the same direction, for which the reference's neighbour-slot rule is undefined).  Synchronises the stream.
+ * fem_midpoints_p2_fill: coord [2][n_n] -> coord_mid [2][n_mid] = (x_from + x_to) / 2 of the first occurrence;
+ *   elem_mid [3][n_e] midpoint index of every element edge (the reference's elem_ed; elem_ext rows 3..5 = elem_mid + n_n);
+ *   edge_el [2][n_mid] the elements of the first and (if shared, else 0) the second occurrence (:1536, :1544);
+ *   surf [3][n_bnd] = (to vertex, from vertex, n_n + midpoint) per boundary edge in midpoint order (:1556, :1586, :1616).
+ * fem_midpoints_p2_destroy frees the handle (after synchronising the stream).                                          */
+int fem_midpoints_p2_count(int64_t n_n, int64_t n_e, const int32_t* elem, void** handle, int64_t* n_mid, int64_t* n_bnd,
+                           int* status, fem_stream stream);
+int fem_midpoints_p2_fill(void* handle, const double* coord, double* coord_mid, int32_t* elem_mid, int32_t* edge_el,
+                          int32_t* surf, fem_stream stream);
+int fem_midpoints_p2_destroy(void* handle, fem_stream stream);
+
 /* launch-shape knobs for benchmarking ("return_map_variant", "assemble_variant", "assemble_warps", "spmv_group", "spmv_blocks_per_sm",
  * "spmv_staged", "peer_timeout_ms", "strain_variant", "assemble_canon");
  * value 0 restores the default.  Results never depend on them.                                     */
