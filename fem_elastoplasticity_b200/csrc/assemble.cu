@@ -816,7 +816,24 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
         else if (nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
       }
     }
-    if (a < A.n_n) {
+    if (MAXDEG >= 7 && MODE != MODE_TANGENT_REF && canon && A.canon == 1 && __all_sync(0xffffffffu, cur.deg == 7)) {
+      // Canonical slice: every node has 7 neighbours, so a lane's two rows are 28 consecutive doubles = seven whole 32-byte
+      // sectors (K_vals 32-byte aligned: checked at launch).  Seven 256-bit stores (STG.256) write each sector once; the
+      // 16-byte stores of the generic path below write every sector in two halves from two instructions.
+      if (FORCE) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
+      double* dst = A.K_vals + cur.base;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        // doubles 4k .. 4k+3 of [row 2a: acc[j][0], acc[j][1], j = 0..6 | row 2a+1: acc[j][2], acc[j][3]]
+        double v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int i = 4 * k + t;
+          v[t] = i < 14 ? acc[(i >> 1) < MAXDEG ? (i >> 1) : 0][i & 1] : acc[((i - 14) >> 1) < MAXDEG ? ((i - 14) >> 1) : 0][2 + ((i - 14) & 1)];
+        }
+        asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+      }
+    } else if (a < A.n_n) {
       const int deg = cur.deg;
       if (FORCE) reinterpret_cast<double2*>(A.F)[a] = make_double2(f0, f1);
       double2* row0 = reinterpret_cast<double2*>(A.K_vals + cur.base);
@@ -1038,6 +1055,7 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   A.stage_box = P->stage_box;
   A.inc_stage = P->inc_stage;
   A.boxw = bw;
+  if (A.canon == 1 && (reinterpret_cast<uintptr_t>(A.K_vals) & 31u) != 0) A.canon = 2;  // 256-bit stores need whole sectors
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
   if ((A.DS && mis(A.DS)) || (A.shear && mis(A.shear)) || (A.bulk && mis(A.bulk)) || (FORCE && mis(A.S))) return -1;  // TMA needs 16-byte aligned rows
   StageMaps M;
@@ -1194,7 +1212,9 @@ static void fill_args(const fem_plan* P, AsmArgs& A) {
   A.nbr_ptr = P->nbr_ptr; A.slice_ptr = P->slice_ptr; A.inc_key = P->inc_key; A.inc_meta = P->inc_meta;
   A.dphi1 = P->dphi1; A.dphi2 = P->dphi2; A.weight = P->weight;
   elastic_coeffs(A.dev2, A.vol);
-  A.canon = g_fem_tuning.assemble_canon != 2;  // tuning key assemble_canon = 2 switches the regular-triangulation fast path off
+  // tuning key assemble_canon: 0 auto = regular-triangulation fast path with 256-bit row stores, 3 = fast path with the
+  // 16-byte stores of the generic path, 2 = fast path off
+  A.canon = g_fem_tuning.assemble_canon == 2 ? 0 : (g_fem_tuning.assemble_canon == 3 ? 2 : 1);
 }
 
 extern "C" int fem_assemble_elastic(const fem_plan* P, const double* shear, const double* bulk, double* K_vals,

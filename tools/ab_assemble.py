@@ -1,5 +1,6 @@
-"""A/B of assembly kernel builds: FEM_B200_LIB=<lib> python tools/ab_assemble.py  ->  one line with the isolated times of
-the fused tangent+force assembly, tangent only and elastic at 16M elements, and a bit-equality check against variant B."""
+"""A/B of assembly kernel builds: FEM_B200_LIB=<lib> python tools/ab_assemble.py [nx] [key=value ...]  ->  one line per
+setting (none: the defaults; each key=value is one fem_set_tuning setting, measured in turn, two rounds) with the isolated
+times of the fused tangent+force assembly, tangent only and elastic at 16M elements, and a bit-equality check against variant B."""
 import json
 import os
 import sys
@@ -33,13 +34,21 @@ def timeit(fn, reps=10):
     return a.elapsed_time(b) / reps
 
 
-out = {"lib": os.path.basename(_lib.LIB_PATH)}
-out["tangent_force_ms"] = timeit(lambda: P.assemble_tangent_force(r["ds"], r["s"], out_k=k, out_f=F))
-kd, Fd = k.clone(), F.clone()
-out["tangent_ms"] = timeit(lambda: P.assemble_tangent(r["ds"], out=k))
-out["elastic_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
-_lib.call("fem_set_tuning", b"assemble_variant", 2)
-kb, Fb = P.assemble_tangent_force(r["ds"], r["s"])
-_lib.call("fem_set_tuning", b"assemble_variant", 0)
-out["equals_variant_B_bits"] = bool(torch.equal(kd, kb) and torch.equal(Fd, Fb))
-print(json.dumps(out))
+settings = [a for a in sys.argv[2:] if "=" in a] or [None]
+for rnd in range(2 if settings != [None] else 1):
+    for setting in settings:
+        if setting:
+            key, val = setting.split("=")
+            _lib.call("fem_set_tuning", key.encode(), int(val))
+        out = {"lib": os.path.basename(_lib.LIB_PATH), "setting": setting, "round": rnd}
+        out["tangent_force_ms"] = timeit(lambda: P.assemble_tangent_force(r["ds"], r["s"], out_k=k, out_f=F))
+        kd, Fd = k.clone(), F.clone()
+        out["tangent_ms"] = timeit(lambda: P.assemble_tangent(r["ds"], out=k))
+        out["elastic_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
+        _lib.call("fem_set_tuning", b"assemble_variant", 2)
+        kb, Fb = P.assemble_tangent_force(r["ds"], r["s"])
+        _lib.call("fem_set_tuning", b"assemble_variant", 0)
+        out["equals_variant_B_bits"] = bool(torch.equal(kd, kb) and torch.equal(Fd, Fb))
+        if setting:
+            _lib.call("fem_set_tuning", setting.split("=")[0].encode(), 0)
+        print(json.dumps(out), flush=True)
