@@ -536,7 +536,8 @@ def run_gpu(args):
                   "h2d_bytes": int(2 * 8 * P.n_dof + 3 * nb + 4 * nb + 4 * nb + 9 * nb + 3 * nb + 8 * P.n_dof + 3 * 8 * P.n_dof),
                   "d2h_bytes": int(3 * nb + (4 + 9 + 4 + 1) * nb + P.n_int + 2 * 8 * P.n_dof),
                   "what": "pythonFEM facade, NumPy in/out per call: strain -> construct_constitutive_problem -> assemble_tangent(direct, DeviceMatrix) "
-                          "-> internal_force -> solve_increment (multigrid CG to rtol) -> stopping_criterion; pageable host arrays"}
+                          "-> internal_force -> solve_increment (multigrid CG to rtol) -> stopping_criterion; the caller's arrays (U, materials, Ep, strain) are pageable, "
+                          "the arrays the facade returns (and gets back as the next call's input) are page-locked"}
         del Kel_h, cp
     # ---- reduce over ranks (max time)
     vec = torch.tensor([total_ms, per["strain"], per["return_map"], per["assembly"], per["pcg"], per["criterion"], e2e_ms,

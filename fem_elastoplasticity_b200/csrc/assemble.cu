@@ -147,6 +147,21 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
     uint32_t meta[MW];
 #pragma unroll
     for (int w = 0; w < MW; ++w) meta[w] = __ldcs(A.inc_meta + (int64_t)w * A.sell_entries + at);
+    // The 4*NP entries this incidence contributes to are distinct (distinct nodes of one element): they are taken out of
+    // shared memory once, accumulated over the element's NQ quadrature points in registers - same order: ascending
+    // (quadrature point, strain row) within the element - and put back, instead of a read-modify-write per point
+    // (48 shared-memory accesses per point for P2, which bounded the kernel).
+    double a4[NP][4];
+    if (MODE != MODE_FORCE_ONLY) {
+#pragma unroll
+      for (int lb = 0; lb < NP; ++lb) {
+        const int byte = lb + 1;
+        const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
+        const double* r0 = acc + (2 * slot) * ACC_LD + lane;
+        const double* r1 = acc + (2 * deg + 2 * slot) * ACC_LD + lane;
+        a4[lb][0] = r0[0]; a4[lb][1] = r0[ACC_LD]; a4[lb][2] = r1[0]; a4[lb][3] = r1[ACC_LD];
+      }
+    }
 #pragma unroll 1
     for (int q = 0; q < NQ; ++q) {
       double tx[3], ty[3];
@@ -156,15 +171,21 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
       if (MODE == MODE_FORCE_ONLY) continue;
 #pragma unroll
       for (int lb = 0; lb < NP; ++lb) {
+        const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+        a4[lb][0] = (a4[lb][0] + tx[0] * b1) + tx[2] * b2;  // K[2a  , 2b  ]
+        a4[lb][1] = (a4[lb][1] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
+        a4[lb][2] = (a4[lb][2] + ty[0] * b1) + ty[2] * b2;  // K[2a+1, 2b  ]
+        a4[lb][3] = (a4[lb][3] + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+      }
+    }
+    if (MODE != MODE_FORCE_ONLY) {
+#pragma unroll
+      for (int lb = 0; lb < NP; ++lb) {
         const int byte = lb + 1;
         const int slot = (meta[byte >> 2] >> (8 * (byte & 3))) & 0xFF;
         double* r0 = acc + (2 * slot) * ACC_LD + lane;
         double* r1 = acc + (2 * deg + 2 * slot) * ACC_LD + lane;
-        const double b1 = pd.d1[lb], b2 = pd.d2[lb];
-        r0[0] = (r0[0] + tx[0] * b1) + tx[2] * b2;            // K[2a  , 2b  ]
-        r0[ACC_LD] = (r0[ACC_LD] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
-        r1[0] = (r1[0] + ty[0] * b1) + ty[2] * b2;            // K[2a+1, 2b  ]
-        r1[ACC_LD] = (r1[ACC_LD] + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+        r0[0] = a4[lb][0]; r0[ACC_LD] = a4[lb][1]; r1[0] = a4[lb][2]; r1[ACC_LD] = a4[lb][3];
       }
     }
   }

@@ -79,6 +79,23 @@ def get_local_basis_volume(el_type, xi):
 
 
 # ------------------------------------------------------------------------------------------------
+_PIN_MIN_BYTES = 1 << 20
+
+
+def _to_numpy(t):
+    """Device tensor -> NumPy array.  Arrays of a megabyte or more are downloaded straight into page-locked memory from
+    torch's caching host allocator and handed out as the NumPy array itself (it keeps the block alive and returns it to the
+    cache when it is freed): the copy runs at the PCIe rate instead of the pageable-memory rate, and when the caller passes
+    the array back into the next call of this module (E -> construct_constitutive_problem, ds -> assemble_tangent,
+    s -> internal_force) the upload does too - the CUDA runtime recognises page-locked source memory by address."""
+    if t.numel() * t.element_size() < _PIN_MIN_BYTES:
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def _plan_of(obj):
     if isinstance(obj, FemPlan):
         return obj
@@ -166,15 +183,15 @@ def construct_constitutive_problem(e, *args, apply_plastic_strain=False):
         ep_dev = torch.as_tensor(np.ascontiguousarray(ep_prev, dtype=np.float64)).cuda()
     r = dp_return_map(e, ep_dev, shear, bulk, eta, c, apply_plastic_strain=apply_plastic_strain, e0=e0, want_lambda=True)
     counts = r["counts"].cpu().numpy()
-    ind_p = r["ind_p"].cpu().numpy().astype(bool)
-    lam = r["lambda"].cpu().numpy().reshape(1, -1)
-    ep = r["ep"].cpu().numpy()
+    ind_p = _to_numpy(r["ind_p"]).view(np.bool_)             # flags are 0/1 bytes
+    lam = _to_numpy(r["lambda"]).reshape(1, -1)
+    ep = _to_numpy(r["ep"])
     if e0 is not None and counts.sum() == 0:
         ep = np.zeros_like(ep)              # tsx early-out (tsx-tunnel/pythonFEM.py:1101-1103): ep_prev is ignored
     elif apply_plastic_strain and ep_prev is not None:
         ep_prev[...] = ep                   # the reference returns ep_prev itself, mutated
         ep = ep_prev
-    out = {'s': r["s"].cpu().numpy(), 'ds': r["ds"].cpu().numpy(), 'ind_p': ind_p,
+    out = {'s': _to_numpy(r["s"]), 'ds': _to_numpy(r["ds"]), 'ind_p': ind_p,
            'lambda_final': None if counts[1] > 0 else lam, 'ep': ep,
            'lambda_apex_intended': lam, 'n_smooth': int(counts[0]), 'n_apex': int(counts[1])}
     return out
@@ -185,7 +202,7 @@ def strain(plan_or_B, U):
     """E = reshape(B @ U(:), (3, n_int), 'F') (:1043); U is (2, n_n)."""
     plan = _plan_of(plan_or_B)
     u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).reshape(-1, order='F'))
-    return plan.strain(u).cpu().numpy()
+    return _to_numpy(plan.strain(u))
 
 
 def assemble_tangent(plan_or_K, ds, mode="reference", D_elast=None, K_elast=None, host_matrix=True):
@@ -206,7 +223,7 @@ def assemble_tangent(plan_or_K, ds, mode="reference", D_elast=None, K_elast=None
 def internal_force(plan_or_B, s):
     """F = B^T vec(w * s[0:3]) as an (n_dof, 1) column (:1058)."""
     plan = _plan_of(plan_or_B)
-    return plan.internal_force(np.asarray(s, dtype=np.float64)[0:3]).cpu().numpy().reshape(-1, 1)
+    return _to_numpy(plan.internal_force(np.asarray(s, dtype=np.float64)[0:3])).reshape(-1, 1)
 
 
 class DeviceMatrix:
@@ -251,9 +268,9 @@ def solve_increment(K_tangent, F, Q, rtol=1e-13, maxit=200000, precond="auto", K
                 cache[key] = None
         if cache[key] is not None:
             x, its, rel = cache[key].solve(K_tangent._fem_vals, plan._f64(rhs), rtol=rtol, maxit=min(maxit, 2000))
-            return x.cpu().numpy().reshape((2, -1), order='F')
+            return _to_numpy(x).reshape((2, -1), order='F')
     x, its, rel = plan.pcg(K_tangent._fem_vals, rhs, mask, rtol=rtol, maxit=maxit)
-    dU = x.cpu().numpy().reshape((2, -1), order='F')
+    dU = _to_numpy(x).reshape((2, -1), order='F')
     return dU
 
 
