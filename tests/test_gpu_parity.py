@@ -318,6 +318,47 @@ def test_assembly_variants_agree_bitwise(fem, golden):
     assert_csr_bits(P.to_scipy_csr(fem["torch"].as_tensor(res[2][3]).cuda()), csr_from(g, "Kt"))
 
 
+def test_canonical_row_stores_any_alignment(fem):
+    """The straight-line path of the regular triangulation writes a node's two rows as seven 256-bit stores when K is
+    32-byte aligned and as 16-byte stores otherwise (and with tuning key assemble_canon = 3); with the path off
+    (assemble_canon = 2) the generic kernel runs.  All four must give the same bits, and the oracle's."""
+    torch = fem["torch"]
+    from fem_elastoplasticity_b200 import _lib
+    m = fo.square_mesh_p1(200, 150, 10.0, 7.5)
+    d1, d2, wf = tables(fo.ElementType.P1)
+    n_e = m["elements"].shape[1]
+    G0, K0 = fo.footing_constants()[:2]
+    G, Kb = G0 * np.ones(n_e), K0 * np.ones(n_e)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    assert P.stage_info()[0] == 1
+    rng = np.random.default_rng(5)
+    ds = rng.standard_normal((9, P.n_int))
+    s = rng.standard_normal((4, P.n_int))
+    big = torch.zeros(P.nnz + 8, dtype=torch.float64, device="cuda")
+    assert big.data_ptr() % 32 == 0
+    res = {}
+    try:
+        for name, canon, off in (("wide", 0, 0), ("wide_misaligned", 0, 2), ("narrow", 3, 0), ("generic", 2, 0)):
+            _lib.call("fem_set_tuning", b"assemble_canon", canon)
+            k = big[off:off + P.nnz]
+            assert k.data_ptr() % 32 == (16 if off else 0)
+            P.assemble_elastic(G, Kb, out=k)
+            kel = k.clone()
+            k.zero_()
+            kt, F = P.assemble_tangent_force(ds, s, out_k=k)
+            res[name] = [t.cpu().numpy() for t in (kel, kt.clone(), F)]
+            k.zero_()
+    finally:
+        _lib.call("fem_set_tuning", b"assemble_canon", 0)
+    for name in ("wide_misaligned", "narrow", "generic"):
+        for a, b in zip(res["wide"], res[name]):
+            assert np.array_equal(a, b), name
+    Ko = fo.elastic_stiffness(m["elements"], m["coordinates"], G, Kb, d1, d2, wf)[0]
+    Kg = P.to_scipy_csr(torch.as_tensor(res["wide"][0]).cuda())
+    Kg.eliminate_zeros()
+    assert_csr_bits(Kg, fo.canonical_csr(Ko))
+
+
 def test_full_size_config4_properties(fem):
     """BASELINE.json config 4 (N=2828, 15 995 168 elements): size-independent properties at the benchmarked size."""
     torch = fem["torch"]
