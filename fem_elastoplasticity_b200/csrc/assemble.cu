@@ -837,7 +837,7 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
         else if (nxt.nb == 2) issue_box<MODE, FORCE>(M, box1, bw, nxt.st1, bar1);
       }
     }
-    if (MAXDEG >= 7 && MODE != MODE_TANGENT_REF && canon && A.canon == 1 && __all_sync(0xffffffffu, cur.deg == 7)) {
+    if (MAXDEG >= 7 && canon && A.canon == 1 && __all_sync(0xffffffffu, cur.deg == 7)) {
       // Canonical slice: every node has 7 neighbours, so a lane's two rows are 28 consecutive doubles = seven whole 32-byte
       // sectors (K_vals 32-byte aligned: checked at launch).  Seven 256-bit stores (STG.256) write each sector once; the
       // 16-byte stores of the generic path below write every sector in two halves from two instructions.
@@ -851,6 +851,11 @@ __global__ void __launch_bounds__(352) assemble_rows_tmap_kernel(const AsmArgs A
         for (int t = 0; t < 4; ++t) {
           const int i = 4 * k + t;
           v[t] = i < 14 ? acc[(i >> 1) < MAXDEG ? (i >> 1) : 0][i & 1] : acc[((i - 14) >> 1) < MAXDEG ? ((i - 14) >> 1) : 0][2 + ((i - 14) & 1)];
+        }
+        if (MODE == MODE_TANGENT_REF) {  // csr_plus_csr: K_elast + correction; K_elast streamed as whole sectors too
+          double k0, k1, k2, k3;
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(k0), "=d"(k1), "=d"(k2), "=d"(k3) : "l"(A.Kel + cur.base + 4 * k));
+          v[0] = k0 + v[0]; v[1] = k1 + v[1]; v[2] = k2 + v[2]; v[3] = k3 + v[3];
         }
         asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
       }
@@ -1076,7 +1081,7 @@ static int launch_assemble_tma(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   A.stage_box = P->stage_box;
   A.inc_stage = P->inc_stage;
   A.boxw = bw;
-  if (A.canon == 1 && (reinterpret_cast<uintptr_t>(A.K_vals) & 31u) != 0) A.canon = 2;  // 256-bit stores need whole sectors
+  if (A.canon == 1 && ((reinterpret_cast<uintptr_t>(A.K_vals) | reinterpret_cast<uintptr_t>(A.Kel)) & 31u) != 0) A.canon = 2;  // 256-bit accesses need whole sectors
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
   if ((A.DS && mis(A.DS)) || (A.shear && mis(A.shear)) || (A.bulk && mis(A.bulk)) || (FORCE && mis(A.S))) return -1;  // TMA needs 16-byte aligned rows
   StageMaps M;
@@ -1176,9 +1181,11 @@ template <int MODE, bool FORCE>
 static int launch_assemble(const fem_plan* P, AsmArgs& A, cudaStream_t st) {
   // variant B (register accumulators) for P1/Q1 meshes of bounded valence; variant A (shared memory) otherwise
   const int variant = g_fem_tuning.assemble_variant;
-  // measured defaults (tools/tune.py, 16M elements): elastic -> one-shot TMA, tangent(+force) -> persistent pipelined TMA,
-  // reference-order tangent (reads K_elast in its write-out) -> register kernel
-  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && MODE != MODE_TANGENT_REF) || (variant == 6 || variant == 7 || variant == 8))) {
+  // measured defaults (tools/tune.py, tools/ab_assemble.py, 16M elements): persistent pipelined TMA kernel; the reference-order
+  // tangent (reads K_elast in its write-out) takes it where the straight-line path with 256-bit accesses covers most slices
+  // (1.14 ms against 1.51 ms of the register kernel), else the register kernel
+  const bool ref_tma = MODE != MODE_TANGENT_REF || (2 * P->stage_canon_slices >= P->n_slices && g_fem_tuning.assemble_canon != 2);
+  if (MODE != MODE_FORCE_ONLY && P->stage_ok && ((variant == 0 && ref_tma) || (variant == 6 || variant == 7 || variant == 8))) {
     const int rc = launch_assemble_tma<MODE == MODE_FORCE_ONLY ? MODE_TANGENT : MODE, FORCE>(P, A, st);
     if (rc >= 0) return rc;  // -1: inputs not 16-byte aligned / too much shared memory -> register kernel
   }

@@ -95,6 +95,7 @@ struct fem_plan {
   // <= FEM_STAGE_RMAX runs of consecutive ids (16-byte aligned), and per incidence its position in the staged buffer
   int stage_ok, stage_boxw;
   int64_t stage_fallback_slices;
+  int64_t stage_canon_slices;  // slices of the reference's regular triangulation (straight-line path of the assembly)
   int32_t* stage_box;    // [n_slices][3]: number of boxes, start element of box 0, of box 1 (TMA path when <= 2 boxes)
   uint32_t* inc_stage;   // [sell_entries]: li | la<<9 | slot0<<11 | slot1<<15 | slot2<<19 | valid<<31, li = box*boxw + offset
   double* geom;          // one allocation [1 + 2*n_p][n_int]: weight, dphi1 rows, dphi2 rows (one TMA box brings all rows)

@@ -455,7 +455,7 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int bo
                           (int)(word & 0x1FF) == li0 + 2 * lane;
     else canon_ok = canon_ok && word == 0u;
   }
-  if (__all_sync(0xffffffffu, canon_ok) && lane == 0) out[0] = nb | 0x100;
+  if (__all_sync(0xffffffffu, canon_ok) && lane == 0) { out[0] = nb | 0x100; atomicAdd(flags + 3, 1); }
 }
 
 
@@ -719,27 +719,28 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     P->stage_ok = 0;
     if (n_p == 3 && P->n_q == 1 && P->max_degree <= 8 && P->max_inc <= 8 && (P->n_int % 2) == 0 && P->n_int >= 64) {
       int* sflags = nullptr;
-      if (cudaMalloc(&sflags, 3 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc sflags"); break; }
-      cudaMemsetAsync(sflags, 0, 3 * sizeof(int), st);
+      if (cudaMalloc(&sflags, 4 * sizeof(int)) != cudaSuccess) { rc = FEM_ERR_CUDA; fem_set_error("cudaMalloc sflags"); break; }
+      cudaMemsetAsync(sflags, 0, 4 * sizeof(int), st);
       if ((rc = dmalloc(P, &P->stage_box, P->n_slices * 3)) != FEM_OK) break;
       if ((rc = dmalloc(P, &P->inc_stage, P->sell_entries)) != FEM_OK) break;
       const unsigned sblocks = (unsigned)((P->n_slices * 32 + threads - 1) / threads);
       build_stage<<<sblocks, threads, 0, st>>>(n_n, P->n_slices, P->n_int, 0, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_box,
                                                P->inc_stage, sflags);
-      int hs[3] = {1, 0, 0};
+      int hs[4] = {1, 0, 0, 0};
       cudaStreamSynchronize(st);
       cudaMemcpy(hs, sflags, sizeof(hs), cudaMemcpyDeviceToHost);
       if (hs[0] == 0 && hs[1] > 0) {
         int boxw = (hs[1] + 1) & ~1;
         if (boxw > FEM_STAGE_MAXBOXW) boxw = FEM_STAGE_MAXBOXW;
         if (boxw < 16) boxw = 16;
-        cudaMemsetAsync(sflags, 0, 3 * sizeof(int), st);
+        cudaMemsetAsync(sflags, 0, 4 * sizeof(int), st);
         build_stage<<<sblocks, threads, 0, st>>>(n_n, P->n_slices, P->n_int, boxw, P->slice_ptr, P->inc_key, P->inc_meta, P->stage_box,
                                                  P->inc_stage, sflags);
         cudaStreamSynchronize(st);
         cudaMemcpy(hs, sflags, sizeof(hs), cudaMemcpyDeviceToHost);
         P->stage_boxw = boxw;
         P->stage_fallback_slices = hs[2];
+        P->stage_canon_slices = hs[3];
         // worth it only when most slices take the TMA path
         if (hs[0] == 0 && (int64_t)hs[2] * 8 <= P->n_slices &&
             fem_encode_rows_map(&P->geom_map, P->geom, P->n_int, 7, boxw) == FEM_OK)

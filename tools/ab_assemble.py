@@ -45,10 +45,15 @@ for rnd in range(2 if settings != [None] else 1):
         kd, Fd = k.clone(), F.clone()
         out["tangent_ms"] = timeit(lambda: P.assemble_tangent(r["ds"], out=k))
         out["elastic_ms"] = timeit(lambda: P.assemble_elastic(G, Kb, out=k))
+        kel = k.clone()
+        k2 = P.empty(P.nnz)
+        out["tangent_ref_ms"] = timeit(lambda: P.assemble_tangent_ref(r["ds"], G, Kb, kel, out=k2))
+        kr = k2.clone()
         _lib.call("fem_set_tuning", b"assemble_variant", 2)
         kb, Fb = P.assemble_tangent_force(r["ds"], r["s"])
+        krb = P.assemble_tangent_ref(r["ds"], G, Kb, kel)
         _lib.call("fem_set_tuning", b"assemble_variant", 0)
-        out["equals_variant_B_bits"] = bool(torch.equal(kd, kb) and torch.equal(Fd, Fb))
+        out["equals_variant_B_bits"] = bool(torch.equal(kd, kb) and torch.equal(Fd, Fb) and torch.equal(kr, krb))
         if setting:
             _lib.call("fem_set_tuning", setting.split("=")[0].encode(), 0)
         print(json.dumps(out), flush=True)
