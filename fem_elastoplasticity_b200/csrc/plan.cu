@@ -465,6 +465,14 @@ __global__ void build_stage(int64_t n_n, int64_t n_slices, int64_t n_int, int bo
 // contiguous ranges (gaps < GAP nodes are bridged); when they fit FEM_SPMV_MAXSEG ranges / FEM_SPMV_CAP nodes, every
 // block gets the position of its column inside the concatenated ranges (nbr_loc), else the tile gathers from global memory.
 // On a structured P1 mesh a tile sees three ranges of 130 nodes (the node rows below, at and above it).
+//
+// Bank phases.  The kernels gather x from the concatenated ranges with 16-byte shared-memory loads, eight lanes (two
+// nodes x four blocks) per wavefront: two entries whose positions agree mod 8 cost a replay, and whether the entries of
+// different ranges collide depends only on the ranges' relative positions mod 8 (ncu on the streaming kernel: every x gather
+// took 8 wavefronts instead of 4, a third of the kernel's shared-memory wavefronts, profiles/r2zz).  So every range after
+// the first is extended backwards by 0-7 nodes (a few more bytes copied), chosen greedily range by range to minimise the
+// collisions of the streaming kernel's access pattern (spmv_stream.cuh: the nodes n and n ^ 2 of an aligned group of
+// eight share a wavefront; blocks 0-3 and 4-7 of a row are separate loads), counted over the tile's own rows.
 // ------------------------------------------------------------------------------------------------
 constexpr int SPMV_WIN = 1 << 16;  // nodes covered by the bitmap
 constexpr int SPMV_GAP = 32;
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(FEM_SPMV_TILE) build_spmv_tiles(int64_t n_n, c
                                                                  uint16_t* __restrict__ nbr_loc, int* n_fallback) {
   __shared__ uint32_t bits[SPMV_WIN / 32];
   __shared__ int s_min, s_max, s_nseg, s_start[FEM_SPMV_MAXSEG], s_len[FEM_SPMV_MAXSEG], s_off[FEM_SPMV_MAXSEG];
+  __shared__ int s_total, s_ok, s_shift[FEM_SPMV_MAXSEG], s_cost[8];
   const int64_t tile = blockIdx.x;
   const int64_t a = tile * FEM_SPMV_TILE + threadIdx.x;
   int p0 = 0, deg = 0;
@@ -517,6 +526,98 @@ __global__ void __launch_bounds__(FEM_SPMV_TILE) build_spmv_tiles(int64_t n_n, c
       }
     }
     const bool ok = window_ok && nseg >= 1 && nseg <= FEM_SPMV_MAXSEG && total <= FEM_SPMV_CAP;
+    s_nseg = ok ? nseg : 0;
+    s_total = total;
+    s_ok = ok;
+    for (int k = 0; k < FEM_SPMV_MAXSEG; ++k) s_shift[k] = 0;
+    if (!ok && hi >= lo) atomicAdd(n_fallback, 1);
+  }
+  __syncthreads();
+  // ---- bank phases: shift of range k (mod 8), greedy over the ranges; thread t with bit 1 clear owns the node pair (t, t ^ 2)
+  {
+    const int nsg = s_nseg;
+    int eloc[16], eseg[16], ne = 0;  // raw position and range of the pair's blocks 0-7 (entry e: node e / 8, block e % 8)
+    const bool owner = (threadIdx.x & 2) == 0;
+    if (nsg > 1 && owner) {
+      for (int h = 0; h < 2; ++h) {
+        const int64_t an = tile * FEM_SPMV_TILE + (threadIdx.x ^ (h ? 2 : 0));
+        int q0 = 0, dg = 0;
+        if (an < n_n) { q0 = nbr_ptr[an]; dg = nbr_ptr[an + 1] - q0; }
+        for (int j = 0; j < 8; ++j) {
+          eloc[8 * h + j] = -1;
+          eseg[8 * h + j] = 0;
+          if (j < dg) {
+            const int c = nbr_idx[q0 + j];
+            for (int k = 0; k < nsg; ++k)
+              if (c >= s_start[k] && c < s_start[k] + s_len[k]) { eloc[8 * h + j] = s_off[k] + (c - s_start[k]); eseg[8 * h + j] = k; }
+          }
+        }
+      }
+      ne = 16;
+    }
+    for (int k = 1; k < nsg; ++k) {
+      if (threadIdx.x < 8) s_cost[threadIdx.x] = 0;
+      __syncthreads();
+      if (ne) {
+        for (int cand = 0; cand < 8; ++cand) {
+          int cost = 0;
+          for (int b = 0; b < 2; ++b) {  // one wavefront: blocks 4b .. 4b+3 of both nodes
+            int unit[8], pos[8], m = 0;
+            for (int h = 0; h < 2; ++h)
+              for (int j = 4 * b; j < 4 * b + 4; ++j) {
+                const int e = 8 * h + j;
+                if (eloc[e] < 0 || eseg[e] > k) continue;
+                const int l = eloc[e] + (eseg[e] == k ? cand : s_shift[eseg[e]]);
+                bool dup = false;
+                for (int t = 0; t < m; ++t) dup = dup || pos[t] == l;
+                if (!dup) { pos[m] = l; unit[m] = l & 7; ++m; }
+              }
+            int worst = 1;
+            for (int t = 0; t < m; ++t) {
+              int mult = 0;
+              for (int r = 0; r < m; ++r) mult += unit[r] == unit[t];
+              worst = max(worst, mult);
+            }
+            cost += worst - 1;
+          }
+          if (cost) atomicAdd(&s_cost[cand], cost);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int best = 0;
+        for (int cand = 1; cand < 8; ++cand)
+          if (s_cost[cand] < s_cost[best]) best = cand;
+        s_shift[k] = best;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const int nseg = s_nseg;
+    bool ok = s_ok != 0;
+    // shift (mod 8) of range k relative to its raw position = sum of the backward extensions of ranges 1 .. k
+    int ext[FEM_SPMV_MAXSEG] = {0, 0, 0, 0}, total = s_total;
+    if (ok && nseg > 1) {
+      int prev = 0, extra = 0;
+      for (int k = 1; k < nseg; ++k) {
+        ext[k] = (s_shift[k] - prev) & 7;
+        prev = s_shift[k];
+        extra += ext[k];
+      }
+      bool fits = total + extra <= FEM_SPMV_CAP;
+      for (int k = 1; k < nseg; ++k) fits = fits && s_start[k] - ext[k] >= s_start[k - 1] + s_len[k - 1];
+      if (!fits)
+        for (int k = 0; k < FEM_SPMV_MAXSEG; ++k) ext[k] = 0;
+      int off = 0;
+      for (int k = 0; k < nseg; ++k) {
+        s_start[k] -= ext[k];
+        s_len[k] += ext[k];
+        s_off[k] = off;
+        off += s_len[k];
+      }
+      total = off;
+    }
     int32_t* d = tile_seg + tile * FEM_SPMV_DESC;
     d[0] = ok ? nseg : 0;
     d[1] = ok ? total : 0;
@@ -529,8 +630,6 @@ __global__ void __launch_bounds__(FEM_SPMV_TILE) build_spmv_tiles(int64_t n_n, c
     d[10] = nbr_ptr[a0];
     d[11] = nbr_ptr[a1] - nbr_ptr[a0];
     atomicMax(n_fallback + 1, d[11]);
-    s_nseg = ok ? nseg : 0;
-    if (!ok && hi >= lo) atomicAdd(n_fallback, 1);
   }
   __syncthreads();
   const int nseg = s_nseg;

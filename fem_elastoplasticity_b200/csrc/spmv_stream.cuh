@@ -75,7 +75,14 @@ __device__ __forceinline__ double spmv_stream(const SpmvStreamArgs A, const VT* 
   static_assert(FEM_SPMV_TILE % NPS == 0, "tile size");
   constexpr int NIN = EPI::N_IN;
   static_assert(NIN <= FEM_STREAM_NIN, "too many staged epilogue vectors");
-  const int tid = threadIdx.x, sub = tid % GROUP, gi = tid / GROUP;
+  const int tid = threadIdx.x, sub = tid % GROUP;
+  // Lane groups -> nodes.  With four lanes per node a warp holds eight consecutive nodes and a 64-bit (128-bit) shared-memory
+  // load is served half (quarter) warp by half warp: the rows of consecutive P1 nodes lie 112 (224) bytes apart, so
+  // neighbouring nodes overlap in half of their banks and every load of matrix values took twice its wavefronts (ncu,
+  // profiles/r2zz).  Nodes two apart do not collide: groups 0-3 of a warp take the even nodes of the eight, groups 4-7
+  // the odd ones, so a quarter warp holds the nodes n and n ^ 2 (the pairing the plan's bank phases assume, plan.cu).
+  const int g_raw = tid / GROUP;
+  const int gi = GROUP == 4 ? ((g_raw & ~7) | ((g_raw & 3) << 1) | ((g_raw >> 2) & 1)) : g_raw;
   // stage layout
   auto stage = [&](int b) { return smem + (size_t)b * S::STAGE; };
   auto vbuf = [&](int b) { return reinterpret_cast<const P2*>(stage(b)); };
