@@ -244,7 +244,7 @@ def strong_scaling_part(args, world, rank, dev, d1, d2, wf, pcg_one_gpu_ms=None)
     mgs = None
     if args.solver == "multigrid":
         from fem_elastoplasticity_b200.mg import MultigridPCG
-        mgs = MultigridPCG(P, mask, part=part, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio).setup(k_el)
+        mgs = MultigridPCG(P, mask, part=part, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio, **({} if args.mg_replicate_below is None else {"replicate_below": args.mg_replicate_below})).setup(k_el)
     evs, info = [], {"its": args.pcg_iters}
 
     def step(rec):
@@ -362,7 +362,7 @@ def run_gpu(args):
     if args.solver == "multigrid":
         from fem_elastoplasticity_b200.mg import MultigridPCG
         try:
-            mgs = MultigridPCG(P, mask, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio).setup(k_el)
+            mgs = MultigridPCG(P, mask, part=part if world > 1 else None, free_mask=P.mask_u8(mesh["Q"]), degree=args.mg_degree, ratio=args.mg_ratio, **({} if args.mg_replicate_below is None else {"replicate_below": args.mg_replicate_below})).setup(k_el)
         except Exception as e:  # noqa: BLE001  (e.g. no symmetric memory on this box: every rank fails at the same collective)
             mgs, solver_note = None, f"multigrid unavailable ({type(e).__name__}: {e}); step timed with {args.pcg_iters} fixed Jacobi-PCG iterations"
             print(solver_note, file=sys.stderr)
@@ -705,6 +705,7 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--mg-degree", type=int, default=2)
     ap.add_argument("--mg-ratio", type=float, default=16.0)
+    ap.add_argument("--mg-replicate-below", type=int, default=None, help="multigrid levels with at most this many nodes are replicated on every rank (default: mg.py's)")
     ap.add_argument("--no-facade-step", action="store_true", help="skip the whole-step timing through the pythonFEM facade (one GPU)")
     ap.add_argument("--facade-synthetic-strain", action="store_true", default=True, help=argparse.SUPPRESS)
     ap.add_argument("--two-level", action="store_true", help="also solve the step's system with the two-level preconditioner of round 1")
