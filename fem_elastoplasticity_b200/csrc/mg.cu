@@ -227,7 +227,12 @@ __global__ void mg_stencil_to_dense_kernel(Geom g, const double* __restrict__ S,
 // ---- smoother / residual on a structured level ------------------------------------------------------------------------
 enum { MG_APPLY = 0, MG_RESID = 1, MG_CHEB = 2, MG_FIRST = 3 };
 
-template <int MODE, class ST>
+// SYM: the level operators are symmetric (Galerkin products of a symmetric matrix), so the block towards the neighbour in
+// direction -k is the transpose of that neighbour's block in direction +k.  The sweep then streams only the upper half of
+// the stencil from HBM - the self block (3 planes: its two off-diagonal entries are equal) and the directions E, NW, N, NE
+// (16 planes): 19 planes = 76 B per node with the FP32 copy instead of 36 planes = 144 B - and takes W, SW, S, SE from the
+// planes of the west neighbour (same warp: L1) and of the row below (read by the CTAs just before: L2).
+template <int MODE, class ST, bool SYM>
 __global__ void __launch_bounds__(256) mg_stencil_kernel(Geom g, int row_lo, int row_hi, const ST* __restrict__ S, const double2* x,
                                                          const double2* __restrict__ b, const double2* __restrict__ dinv, double2* d,
                                                          double2* out, double c1, double c2) {
@@ -248,11 +253,26 @@ __global__ void __launch_bounds__(256) mg_stencil_kernel(Geom g, int row_lo, int
     const int dx = s % 3 - 1, dy = s / 3 - 1;
     const bool v = (i + dx >= 0) && (i + dx < g.nxn) && (j + dy >= 0) && (j + dy < g.nrows);
     const double2 xv = v ? x[node + dy * g.nxn + dx] : make_double2(0.0, 0.0);
-    const ST* sp = S + (int64_t)(4 * s) * g.n + node;
-    y0 = fma((double)__ldcs(sp), xv.x, y0);
-    y0 = fma((double)__ldcs(sp + g.n), xv.y, y0);
-    y1 = fma((double)__ldcs(sp + 2 * g.n), xv.x, y1);
-    y1 = fma((double)__ldcs(sp + 3 * g.n), xv.y, y1);
+    if (SYM && s < 4) {  // block (node -> node + off) = transpose of the block (node + off -> node) stored with the neighbour
+      const ST* sp = S + (int64_t)(4 * (8 - s)) * g.n + (v ? node + dy * g.nxn + dx : node);
+      y0 = fma((double)__ldg(sp), xv.x, y0);
+      y0 = fma((double)__ldg(sp + 2 * g.n), xv.y, y0);
+      y1 = fma((double)__ldg(sp + g.n), xv.x, y1);
+      y1 = fma((double)__ldg(sp + 3 * g.n), xv.y, y1);
+    } else if (SYM) {    // own upper half: ordinary cached loads - the neighbours read these planes again
+      const ST* sp = S + (int64_t)(4 * s) * g.n + node;
+      const double s01 = (double)__ldg(sp + g.n);
+      y0 = fma((double)__ldg(sp), xv.x, y0);
+      y0 = fma(s01, xv.y, y0);
+      y1 = fma(s == 4 ? s01 : (double)__ldg(sp + 2 * g.n), xv.x, y1);
+      y1 = fma((double)__ldg(sp + 3 * g.n), xv.y, y1);
+    } else {
+      const ST* sp = S + (int64_t)(4 * s) * g.n + node;
+      y0 = fma((double)__ldcs(sp), xv.x, y0);
+      y0 = fma((double)__ldcs(sp + g.n), xv.y, y0);
+      y1 = fma((double)__ldcs(sp + 2 * g.n), xv.x, y1);
+      y1 = fma((double)__ldcs(sp + 3 * g.n), xv.y, y1);
+    }
   }
   if (MODE == MG_APPLY) {
     out[node] = make_double2(y0, y1);
@@ -652,14 +672,19 @@ int launch_stencil(const fem_mg_level& L, const double* x, double* out, double c
   const Geom g = geom_of(L);
   const int64_t items = (int64_t)(L.own_hi - L.own_lo) * L.nxn;
   if (items <= 0) return FEM_OK;
-  if (L.S32 && MODE != MG_FIRST)
-    mg_stencil_kernel<MODE, float><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, L.S32, reinterpret_cast<const double2*>(x),
-                                                                    reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv),
-                                                                    reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2);
-  else
-    mg_stencil_kernel<MODE, double><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, L.S, reinterpret_cast<const double2*>(x),
-                                                                     reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv),
-                                                                     reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2);
+  const bool sym = g_fem_tuning.mg_stencil_sym != 2 && MODE != MG_FIRST;
+#define MG_STENCIL(ST, SYMM, SPTR)                                                                                              \
+  mg_stencil_kernel<MODE, ST, SYMM><<<grid_for(items), 256, 0, st>>>(g, L.own_lo, L.own_hi, SPTR, reinterpret_cast<const double2*>(x), \
+                                                                     reinterpret_cast<const double2*>(L.b), reinterpret_cast<const double2*>(L.dinv), \
+                                                                     reinterpret_cast<double2*>(L.d), reinterpret_cast<double2*>(out), c1, c2)
+  if (L.S32 && MODE != MG_FIRST) {
+    if (sym) MG_STENCIL(float, true, L.S32);
+    else MG_STENCIL(float, false, L.S32);
+  } else {
+    if (sym) MG_STENCIL(double, true, L.S);
+    else MG_STENCIL(double, false, L.S);
+  }
+#undef MG_STENCIL
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -853,7 +878,7 @@ extern "C" int fem_mg_stencil_apply(int nxn, int nrows, int row_lo, int row_hi, 
   const Geom g{nxn, nrows, 0, nrows, (int64_t)nxn * nrows};
   const int64_t items = (int64_t)(row_hi - row_lo) * nxn;
   if (items <= 0) return FEM_OK;
-  mg_stencil_kernel<MG_APPLY, double><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(g, row_lo, row_hi, S, reinterpret_cast<const double2*>(x), nullptr,
+  mg_stencil_kernel<MG_APPLY, double, false><<<grid_for(items), 256, 0, (cudaStream_t)stream>>>(g, row_lo, row_hi, S, reinterpret_cast<const double2*>(x), nullptr,
                                                                                  nullptr, nullptr, reinterpret_cast<double2*>(y), 0.0, 0.0);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;

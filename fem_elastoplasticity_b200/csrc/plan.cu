@@ -33,6 +33,7 @@ extern "C" int fem_set_tuning(const char* key, int value) {
   else if (!strcmp(key, "peer_nowait")) g_fem_tuning.peer_nowait = value;
   else if (!strcmp(key, "strain_variant")) g_fem_tuning.strain_variant = value;
   else if (!strcmp(key, "assemble_canon")) g_fem_tuning.assemble_canon = value;
+  else if (!strcmp(key, "mg_stencil_sym")) g_fem_tuning.mg_stencil_sym = value;
   else {
     fem_set_error("unknown tuning key %s", key);
     return FEM_ERR_INVALID_ARG;

@@ -21,6 +21,9 @@ k_el = P.assemble_elastic(G, Kb)
 r = dp_return_map(meshgen.synthetic_strain_global(P.n_int, 0), None, G, Kb, eta, c)
 k_tan, F = P.assemble_tangent_force(r["ds"], r["s"])
 mask = P.mask_u8(m["Q"])
+for setting in [a for a in sys.argv[3:] if "=" in a]:          # tuning settings, e.g. mg_stencil_sym=2
+    from fem_elastoplasticity_b200 import _lib
+    _lib.call("fem_set_tuning", setting.split("=")[0].encode(), int(setting.split("=")[1]))
 M = mg.MultigridPCG(P, mask, use_graph=False).setup(k_el)
 torch.cuda.synchronize()
 M.solve(k_tan, -F, iters=iters)
