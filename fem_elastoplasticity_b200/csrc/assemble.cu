@@ -20,6 +20,8 @@ struct AsmArgs {
   const double* dphi1;
   const double* dphi2;
   const double* weight;
+  const double* geom_rec;  // [n_int][geom_rs] geometry records (plan: direct-load kernels) or nullptr
+  int geom_rs;
   // mode inputs
   const double* shear;  // MODE 0, 2
   const double* bulk;   // MODE 0, 2
@@ -54,14 +56,12 @@ struct PointData {
 };
 
 template <int NP, int MODE, bool FORCE>
+__device__ __forceinline__ void load_point_geom(const AsmArgs& A, int64_t g, PointData<NP, MODE, FORCE>& P);
+
+template <int NP, int MODE, bool FORCE>
 __device__ __forceinline__ void load_point(const AsmArgs& A, int64_t g, PointData<NP, MODE, FORCE>& P) {
   const int64_t n_int = A.n_int;
-  P.w = A.weight[g];
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    P.d1[p] = A.dphi1[(int64_t)p * n_int + g];
-    P.d2[p] = A.dphi2[(int64_t)p * n_int + g];
-  }
+  load_point_geom<NP, MODE, FORCE>(A, g, P);
   if (MODE == MODE_ELASTIC) {
     P.raw[0] = A.shear[g];
     P.raw[1] = A.bulk[g];
@@ -77,6 +77,71 @@ __device__ __forceinline__ void load_point(const AsmArgs& A, int64_t g, PointDat
     P.s[0] = A.S[g];
     P.s[1] = A.S[n_int + g];
     P.s[2] = A.S[2 * n_int + g];
+  }
+}
+
+// The direct-load kernels (variants A and B) were bound by L2 sector traffic on elements with several quadrature points
+// (ncu, P2: 835 M sectors per launch, L1 hit rate 3 %): a lane read the 1 + 2 NP + 9 values of a point from as many
+// different rows of the [row][n_int] arrays, one 32-byte sector each for 8 useful bytes, and by the time the next point of
+// the same element wanted the neighbouring 8 bytes the sector had left L1.  Two changes, same values and same arithmetic:
+//   * the geometry of a point comes from a record [weight, dphi1[NP], dphi2[NP], padding] of the plan (geom_rec), read with
+//     256-bit loads: (1 + 2 NP) / 4 whole sectors instead of 1 + 2 NP partial ones;
+//   * the material / tangent-operator / stress rows of QC consecutive points of the element are loaded row by row before the
+//     points are processed, so that the loads of one row hit the sector its first load brought in.
+template <int NP>
+__device__ __forceinline__ void load_geom_record(const AsmArgs& A, int64_t g, double& w, double (&d1)[NP], double (&d2)[NP]) {
+  constexpr int NV = 1 + 2 * NP, RS = (NV + 3) & ~3;
+  double v[RS];
+  const double* rec = A.geom_rec + g * RS;
+#pragma unroll
+  for (int k = 0; k < RS; k += 4)
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(rec + k));
+  w = v[0];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    d1[p] = v[1 + p];
+    d2[p] = v[1 + NP + p];
+  }
+}
+
+// rows of QC consecutive points g0 .. g0 + QC - 1 (only the first `n` exist), row by row
+template <int NP, int MODE, bool FORCE, int QC>
+__device__ __forceinline__ void load_rows_chunk(const AsmArgs& A, int64_t g0, int n, PointData<NP, MODE, FORCE> (&P)[QC]) {
+  const int64_t n_int = A.n_int;
+  if (MODE == MODE_ELASTIC || MODE == MODE_TANGENT_REF) {
+    constexpr int o = MODE == MODE_TANGENT_REF ? 9 : 0;
+#pragma unroll
+    for (int q = 0; q < QC; ++q) if (q < n) P[q].raw[o] = A.shear[g0 + q];
+#pragma unroll
+    for (int q = 0; q < QC; ++q) if (q < n) P[q].raw[MODE == MODE_FORCE_ONLY ? 0 : o + 1] = A.bulk[g0 + q];
+  }
+  if (MODE == MODE_TANGENT || MODE == MODE_TANGENT_REF) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int q = 0; q < QC; ++q) if (q < n) P[q].raw[MODE == MODE_TANGENT || MODE == MODE_TANGENT_REF ? k : 0] = A.DS[(int64_t)k * n_int + g0 + q];
+  }
+  if (FORCE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int q = 0; q < QC; ++q) if (q < n) P[q].s[FORCE ? k : 0] = A.S[(int64_t)k * n_int + g0 + q];
+  }
+}
+
+// geometry of one point: record (plan) when there is one, else the row arrays
+template <int NP, int MODE, bool FORCE>
+__device__ __forceinline__ void load_point_geom(const AsmArgs& A, int64_t g, PointData<NP, MODE, FORCE>& P) {
+  if (A.geom_rec) {
+    load_geom_record<NP>(A, g, P.w, P.d1, P.d2);
+  } else {
+    const int64_t n_int = A.n_int;
+    P.w = A.weight[g];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      P.d1[p] = A.dphi1[(int64_t)p * n_int + g];
+      P.d2[p] = A.dphi2[(int64_t)p * n_int + g];
+    }
   }
 }
 
@@ -162,20 +227,27 @@ __global__ void __launch_bounds__(128) assemble_rows_kernel(const AsmArgs A) {
         a4[lb][0] = r0[0]; a4[lb][1] = r0[ACC_LD]; a4[lb][2] = r1[0]; a4[lb][3] = r1[ACC_LD];
       }
     }
+    constexpr int QC = NQ >= 4 ? 4 : NQ;  // points whose rows are loaded together (load_rows_chunk)
 #pragma unroll 1
-    for (int q = 0; q < NQ; ++q) {
-      double tx[3], ty[3];
-      PointData<NP, MODE, FORCE> pd;
-      load_point<NP, MODE, FORCE>(A, e * NQ + q, pd);
-      point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
-      if (MODE == MODE_FORCE_ONLY) continue;
+    for (int q0 = 0; q0 < NQ; q0 += QC) {
+      PointData<NP, MODE, FORCE> pc[QC];
+      load_rows_chunk<NP, MODE, FORCE, QC>(A, e * NQ + q0, NQ - q0, pc);
 #pragma unroll
-      for (int lb = 0; lb < NP; ++lb) {
-        const double b1 = pd.d1[lb], b2 = pd.d2[lb];
-        a4[lb][0] = (a4[lb][0] + tx[0] * b1) + tx[2] * b2;  // K[2a  , 2b  ]
-        a4[lb][1] = (a4[lb][1] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
-        a4[lb][2] = (a4[lb][2] + ty[0] * b1) + ty[2] * b2;  // K[2a+1, 2b  ]
-        a4[lb][3] = (a4[lb][3] + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+      for (int qq = 0; qq < QC; ++qq) {
+        if (q0 + qq >= NQ) break;
+        double tx[3], ty[3];
+        PointData<NP, MODE, FORCE>& pd = pc[qq];
+        load_point_geom<NP, MODE, FORCE>(A, e * NQ + q0 + qq, pd);
+        point_terms<NP, MODE, FORCE>(A, pd, la, tx, ty, f0, f1);
+        if (MODE == MODE_FORCE_ONLY) continue;
+#pragma unroll
+        for (int lb = 0; lb < NP; ++lb) {
+          const double b1 = pd.d1[lb], b2 = pd.d2[lb];
+          a4[lb][0] = (a4[lb][0] + tx[0] * b1) + tx[2] * b2;  // K[2a  , 2b  ]
+          a4[lb][1] = (a4[lb][1] + tx[1] * b2) + tx[2] * b1;  // K[2a  , 2b+1]
+          a4[lb][2] = (a4[lb][2] + ty[0] * b1) + ty[2] * b2;  // K[2a+1, 2b  ]
+          a4[lb][3] = (a4[lb][3] + ty[1] * b2) + ty[2] * b1;  // K[2a+1, 2b+1]
+        }
       }
     }
     if (MODE != MODE_FORCE_ONLY) {
@@ -1239,6 +1311,7 @@ static void fill_args(const fem_plan* P, AsmArgs& A) {
   A.n_n = P->n_n; A.n_e = P->n_e; A.n_int = P->n_int; A.n_slices = P->n_slices; A.sell_entries = P->sell_entries;
   A.nbr_ptr = P->nbr_ptr; A.slice_ptr = P->slice_ptr; A.inc_key = P->inc_key; A.inc_meta = P->inc_meta;
   A.dphi1 = P->dphi1; A.dphi2 = P->dphi2; A.weight = P->weight;
+  A.geom_rec = P->geom_rec; A.geom_rs = P->geom_rs;
   elastic_coeffs(A.dev2, A.vol);
   // tuning key assemble_canon: 0 auto = regular-triangulation fast path with 256-bit row stores, 3 = fast path with the
   // 16-byte stores of the generic path, 2 = fast path off

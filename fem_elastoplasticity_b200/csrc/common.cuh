@@ -100,6 +100,10 @@ struct fem_plan {
   int32_t* stage_box;    // [n_slices][3]: number of boxes, start element of box 0, of box 1 (TMA path when <= 2 boxes)
   uint32_t* inc_stage;   // [sell_entries]: li | la<<9 | slot0<<11 | slot1<<15 | slot2<<19 | valid<<31, li = box*boxw + offset
   double* geom;          // one allocation [1 + 2*n_p][n_int]: weight, dphi1 rows, dphi2 rows (one TMA box brings all rows)
+  double* geom_rec;      // [n_int][geom_rs] records (weight, dphi1[n_p], dphi2[n_p], padding to a multiple of 4 doubles) for the
+                         // direct-load assembly kernels (P2 / Q1 / Q2, unstructured P1): a point's geometry in 2-5 whole sectors instead
+                         // of 1 + 2 n_p sectors of the row arrays; nullptr when the TMA-staged P1 kernel serves the mesh
+  int geom_rs;
   CUtensorMap geom_map;
   // x-staging plan of the SpMV (spmv.cuh): per tile of FEM_SPMV_TILE consecutive nodes the referenced columns as
   // <= FEM_SPMV_MAXSEG contiguous node ranges (brought into shared memory by bulk async copies), and per 2x2 block the

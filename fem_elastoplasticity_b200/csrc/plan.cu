@@ -688,6 +688,16 @@ static int dmalloc(fem_plan* p, T** ptr, int64_t count) {
     if (_rc != FEM_OK) return _rc; \
   } while (0)
 
+// geometry records of the direct-load assembly kernels (common.cuh: geom_rec): one thread per (point, record entry)
+__global__ void build_geom_records(int64_t n_int, int n_p, int rs, const double* __restrict__ geom, double* __restrict__ rec) {
+  const int64_t total = n_int * rs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = t / rs;
+    const int k = (int)(t - g * rs);
+    rec[t] = k < 1 + 2 * n_p ? geom[(int64_t)k * n_int + g] : 0.0;
+  }
+}
+
 __global__ void interleave_coord(int64_t n_n, const double* __restrict__ coord, double2* __restrict__ out) {
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_n; a += (int64_t)gridDim.x * blockDim.x)
     out[a] = make_double2(coord[a], coord[n_n + a]);
@@ -848,6 +858,12 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
       }
       cudaFree(sflags);
     }
+    P->geom_rec = nullptr;
+    P->geom_rs = (1 + 2 * n_p + 3) & ~3;
+    if (!P->stage_ok) {  // the direct-load assembly kernels serve this mesh
+      if ((rc = dmalloc(P, &P->geom_rec, P->n_int * P->geom_rs)) != FEM_OK) break;
+      build_geom_records<<<grid(P->n_int * P->geom_rs), threads, 0, st>>>(P->n_int, n_p, P->geom_rs, P->geom, P->geom_rec);
+    }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fem_set_error("plan build failed: %s", cudaGetErrorString(e)); rc = FEM_ERR_CUDA; break; }
     cudaMemcpy(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost);
@@ -910,7 +926,7 @@ extern "C" int fem_plan_destroy(fem_plan* P) {
   cudaFree(P->stage_box); cudaFree(P->inc_stage); cudaFree(P->tile_seg); cudaFree(P->nbr_loc);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
-  cudaFree(P->geom); cudaFree(P->dscratch); cudaFree(P->coord2);
+  cudaFree(P->geom); cudaFree(P->dscratch); cudaFree(P->coord2); cudaFree(P->geom_rec);
   delete P;
   return FEM_OK;
 }
