@@ -67,8 +67,14 @@ class TwoLevelPCG:
         (x0, y0), (x1, y1) = lo.tolist(), hi.tolist()
         lx, ly = max(x1 - x0, 1e-300), max(y1 - y0, 1e-300)
         ncx, ncy = (max(1, round(nc * lx / ly)), nc) if lx >= ly else (nc, max(1, round(nc * ly / lx)))
+        asked = (ncx, ncy)
         while 2 * (ncx + 1) * (ncy + 1) > max_coarse_dofs:      # keep the dense inverse small (n_c^2 doubles)
             ncx, ncy = max(1, int(ncx * 0.9)), max(1, int(ncy * 0.9))
+        self.grid_requested = asked
+        if (ncx, ncy) != asked:                                  # not silently: the iteration count grows with H/h
+            import warnings
+            warnings.warn(f"TwoLevelPCG: coarse grid {asked[0]}x{asked[1]} shrunk to {ncx}x{ncy} to keep the dense coarse inverse at "
+                          f"<= {max_coarse_dofs} DOFs (max_coarse_dofs); expect more CG iterations", RuntimeWarning, stacklevel=2)
         self.grid = (float(x0), float(y0), float(lx / ncx), float(ly / ncy), int(ncx), int(ncy))
         self.ncd = 2 * (ncx + 1) * (ncy + 1)
         n = self.ops.n_dof
