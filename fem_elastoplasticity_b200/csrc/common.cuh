@@ -92,6 +92,8 @@ struct fem_plan {
   double2* coord2;  // [n_n] node coordinates (x, y) interleaved: one 16-byte gather per node (P1 strain kernel)
   // scratch
   double* dscratch;  // small device scratch: 8 doubles (PCG scalars) + FEM_SLICE_COUNTERS 8-byte counters
+  double* red_partials;  // [3][FEM_RED_MAXB] block sums + ticket counter of the order-deterministic dot products of this plan's SpMV
+  unsigned* red_ticket;
   // TMA staging data of the P1 assembly kernel (valid when stage_ok): per 32-node slice the touched elements as
   // <= FEM_STAGE_RMAX runs of consecutive ids (16-byte aligned), and per incidence its position in the staged buffer
   int stage_ok, stage_boxw;
@@ -154,6 +156,48 @@ __device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 doub
   __syncthreads();
   return v;
 }
+
+// Order-deterministic grid-wide sums.  Every block stores its sums (block_sum: a fixed tree) into its own slot of a buffer;
+// the block that draws the last ticket adds the slots in a fixed order (lane-strided, then the butterfly) and adds the
+// totals to their destinations - one addition by one thread, so `+=` onto a slot another kernel has zeroed keeps its
+// meaning and the result does not depend on the order in which the blocks finish (atomicAdd of the block sums did).
+// Grids larger than the buffer, or a missing buffer, fall back to atomics.  One buffer serves kernels that are ordered
+// on a stream (the ticket counter wraps back to zero in every launch).
+#define FEM_RED_MAXB 8192
+struct FemRedBuf {
+  double* partials;  // [3][FEM_RED_MAXB]
+  unsigned* ticket;
+};
+template <int N>
+__device__ __forceinline__ void ordered_accumulate(const double (&v)[N], double* const (&dst)[N], const FemRedBuf rb) {
+  static_assert(N <= 3, "partial buffer holds three sums per block");
+  if (gridDim.x > FEM_RED_MAXB || rb.partials == nullptr) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) atomicAdd(dst[i], v[i]);
+    }
+    return;
+  }
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) rb.partials[i * FEM_RED_MAXB + blockIdx.x] = v[i];
+    __threadfence();
+    s_last = atomicInc(rb.ticket, gridDim.x - 1) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double t = 0.0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) t += __ldcg(rb.partials + i * FEM_RED_MAXB + b);
+      t = warp_sum(t);
+      if (threadIdx.x == 0) *dst[i] += t;
+    }
+  }
+}
+FemRedBuf fem_red_buffer_for(const void* key, cudaStream_t st);  // solver.cu: buffer registered for a scalar array (created on first use)
 
 // streaming (read-once) loads/stores: keep them out of L1 so that L1 serves the gathers
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }

@@ -822,6 +822,9 @@ static int build_plan(fem_plan* P, const int32_t* elem, const double* coord, cud
     P->dphi1 = P->geom + P->n_int;
     P->dphi2 = P->geom + (int64_t)(1 + n_p) * P->n_int;
     if ((rc = dmalloc(P, &P->dscratch, 8 + FEM_SLICE_COUNTERS)) != FEM_OK) break;
+    if ((rc = dmalloc(P, &P->red_partials, 3 * FEM_RED_MAXB + 8)) != FEM_OK) break;
+    P->red_ticket = reinterpret_cast<unsigned*>(P->red_partials + 3 * FEM_RED_MAXB);
+    cudaMemsetAsync(P->red_ticket, 0, 8 * sizeof(double), st);
     if ((rc = launch_geometry(P, coord, flags + 3, st)) != FEM_OK) break;
     if ((rc = dmalloc(P, &P->coord2, n_n)) != FEM_OK) break;
     interleave_coord<<<grid(n_n), threads, 0, st>>>(n_n, coord, P->coord2);
@@ -926,7 +929,7 @@ extern "C" int fem_plan_destroy(fem_plan* P) {
   cudaFree(P->stage_box); cudaFree(P->inc_stage); cudaFree(P->tile_seg); cudaFree(P->nbr_loc);
   cudaFree(P->elem); cudaFree(P->nbr_ptr); cudaFree(P->nbr_idx); cudaFree(P->row_ptr); cudaFree(P->col_idx);
   cudaFree(P->inc_cnt); cudaFree(P->slice_ptr); cudaFree(P->inc_key); cudaFree(P->inc_meta);
-  cudaFree(P->geom); cudaFree(P->dscratch); cudaFree(P->coord2); cudaFree(P->geom_rec);
+  cudaFree(P->geom); cudaFree(P->dscratch); cudaFree(P->coord2); cudaFree(P->geom_rec); cudaFree(P->red_partials);
   delete P;
   return FEM_OK;
 }

@@ -7,16 +7,43 @@
 // (nbr_idx, 4 B per 4 values) instead of once per value, so a sweep moves 8 B/nnz of values plus
 // 1 B/nnz of indices instead of CSR's 12 B/nnz.  Row values are read as coalesced double2, x is
 // gathered as one double2 per block through L1/L2.
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "spmv.cuh"
 #include "spmv_stream.cuh"
+
+// Partial-sum buffers of the order-deterministic reductions of the PCG vector kernels (common.cuh: ordered_accumulate), one per
+// scalar array the caller passes (fem_pcg_*'s `scal`): created on first use - fem_pcg_init, always outside a stream capture -
+// and kept for the life of the process (196 KB each; a solver object has one scalar array).
+FemRedBuf fem_red_buffer_for(const void* key, cudaStream_t st) {
+  static std::mutex mu;
+  static std::unordered_map<uintptr_t, FemRedBuf> map;
+  std::lock_guard<std::mutex> lock(mu);
+  const auto it = map.find(reinterpret_cast<uintptr_t>(key));
+  if (it != map.end()) return it->second;
+  FemRedBuf rb{nullptr, nullptr};
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return rb;  // no allocation inside a capture: atomics
+  double* p = nullptr;
+  if (cudaMalloc(&p, (3 * FEM_RED_MAXB + 8) * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    return rb;
+  }
+  rb.partials = p;
+  rb.ticket = reinterpret_cast<unsigned*>(p + 3 * FEM_RED_MAXB);
+  cudaMemsetAsync(rb.ticket, 0, 8 * sizeof(double), st);
+  map.emplace(reinterpret_cast<uintptr_t>(key), rb);
+  return rb;
+}
 
 template <int GROUP, int U>
 __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr,
                                                           const int32_t* __restrict__ nbr_idx,
                                                           const double* __restrict__ vals, const double* __restrict__ x,
                                                           double* __restrict__ y, const uint8_t* __restrict__ mask,
-                                                          double* dot_out, double* zero_a, double* zero_b) {
+                                                          double* dot_out, double* zero_a, double* zero_b, const FemRedBuf rb) {
   __shared__ double red[32];
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // scalar housekeeping for the PCG (see fem_pcg_spmv_dot)
     if (zero_a) *zero_a = 0.0;
@@ -24,8 +51,9 @@ __global__ void __launch_bounds__(256) spmv_blocks_kernel(int64_t n_n, const int
   }
   double dot = spmv_rows<GROUP, U>(n_n, nbr_ptr, nbr_idx, vals, x, y, mask, dot_out != nullptr);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
@@ -35,7 +63,8 @@ __global__ void __launch_bounds__(FEM_SPMV_THREADS) spmv_tiles_kernel(int64_t n_
                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                          const int32_t* __restrict__ tile_seg, const double* __restrict__ vals,
                                                          const double* __restrict__ x, double* __restrict__ y,
-                                                         const uint8_t* __restrict__ mask, double* dot_out, double* zero_a, double* zero_b) {
+                                                         const uint8_t* __restrict__ mask, double* dot_out, double* zero_a, double* zero_b,
+                                                         const FemRedBuf rb) {
   __shared__ double red[32];
   __shared__ SpmvTileSmem sm;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -44,15 +73,17 @@ __global__ void __launch_bounds__(FEM_SPMV_THREADS) spmv_tiles_kernel(int64_t n_
   }
   double dot = spmv_tiles<GROUP, false>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, y, mask, dot_out != nullptr, sm);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
 // every operand streamed through shared memory by bulk async copies (spmv_stream.cuh); one persistent CTA per SM
 template <int GROUP>
 __global__ void __launch_bounds__(FEM_STREAM_THREADS, 1) spmv_stream_kernel(const SpmvStreamArgs A, const double* __restrict__ vals, const double* __restrict__ x,
-                                                                        const SpmvStreamStore epi, double* dot_out, double* zero_a, double* zero_b) {
+                                                                        const SpmvStreamStore epi, double* dot_out, double* zero_a, double* zero_b,
+                                                                        const FemRedBuf rb) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   __shared__ double red[32];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -61,8 +92,9 @@ __global__ void __launch_bounds__(FEM_STREAM_THREADS, 1) spmv_stream_kernel(cons
   }
   double dot = spmv_stream<GROUP, false, double>(A, vals, x, epi, stream_smem);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
@@ -72,6 +104,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
                   (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "K_vals, x, y must be 16-byte aligned");
   const SpmvShape sh = spmv_shape(P);
   const int threads = 256, group = sh.group, unroll = sh.unroll;
+  const FemRedBuf rb{P->red_partials, P->red_ticket};  // order-deterministic x'y (one SpMV with a dot product per plan at a time)
   // default: every operand streamed through shared memory by a producer warp (0.380 ms at 16M elements; the register-fed
   // kernel below: 0.455 ms; tuning key spmv_staged = 2 selects it, 1 the round-1 gather kernel)
   if (g_fem_tuning.spmv_staged == 0 && spmv_can_stream(P) && (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15u) == 0)) {
@@ -86,7 +119,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
       FEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_stream_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    spmv_stream_kernel<G><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K_vals, x, epi, dot, zero_a, zero_b);            \
+    spmv_stream_kernel<G><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K_vals, x, epi, dot, zero_a, zero_b, rb);        \
   } while (0)
     if (group == 4) SPMVS(4);
     else if (group == 8) SPMVS(8);
@@ -97,7 +130,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
   }
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
-#define SPMVT(G) spmv_tiles_kernel<G><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b)
+#define SPMVT(G) spmv_tiles_kernel<G><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K_vals, x, y, mask, dot, zero_a, zero_b, rb)
     if (group == 4) SPMVT(4);
     else if (group == 8) SPMVT(8);
     else SPMVT(16);
@@ -106,7 +139,7 @@ static int launch_spmv(const fem_plan* P, const double* K_vals, const double* x,
     return FEM_OK;
   }
   const unsigned blocks = sh.blocks;
-#define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b)
+#define SPMV(G, UU) spmv_blocks_kernel<G, UU><<<blocks, threads, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, x, y, mask, dot, zero_a, zero_b, rb)
 #define SPMV_U(G) do { if (unroll == 1) SPMV(G, 1); else if (unroll == 2) SPMV(G, 2); else SPMV(G, 4); } while (0)
   if (group == 4) SPMV_U(4);
   else if (group == 8) SPMV_U(8);
@@ -160,7 +193,7 @@ __device__ __forceinline__ int rz_new_slot(int it) { return (it & 1) ? 0 : 2; }
 
 __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* __restrict__ rhs, const double* __restrict__ Kx0,
                                                        const uint8_t* __restrict__ mask, const double* __restrict__ minv,
-                                                       double* __restrict__ r, double* __restrict__ p, double* scal) {
+                                                       double* __restrict__ r, double* __restrict__ p, double* scal, const FemRedBuf rb) {
   __shared__ double red[32];
   double rz = 0.0, rr = 0.0, bb = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -174,19 +207,14 @@ __global__ void __launch_bounds__(256) pcg_init_kernel(int64_t n, const double* 
     rr = fma(ri, ri, rr);
     bb = fma(b, b, bb);
   }
-  rz = block_sum(rz, red);
-  rr = block_sum(rr, red);
-  bb = block_sum(bb, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(scal + 0, rz);
-    atomicAdd(scal + 1, rr);
-    atomicAdd(scal + 4, bb);
-  }
+  const double v[3] = {block_sum(rz, red), block_sum(rr, red), block_sum(bb, red)};
+  double* const dst[3] = {scal + 0, scal + 1, scal + 4};
+  ordered_accumulate<3>(v, dst, rb);
 }
 
 __global__ void __launch_bounds__(256) pcg_update_xr_kernel(int64_t n2, const double2* __restrict__ p, const double2* __restrict__ q,
                                                             const double2* __restrict__ minv, double2* __restrict__ x,
-                                                            double2* __restrict__ r, double* scal, int it) {
+                                                            double2* __restrict__ r, double* scal, int it, const FemRedBuf rb) {
   __shared__ double red[32];
   const double rz_old = scal[rz_old_slot(it)], pq = scal[3];
   const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
@@ -205,12 +233,9 @@ __global__ void __launch_bounds__(256) pcg_update_xr_kernel(int64_t n2, const do
     rr = fma(ri.x, ri.x, rr);
     rr = fma(ri.y, ri.y, rr);
   }
-  rz = block_sum(rz, red);
-  rr = block_sum(rr, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(scal + rz_new_slot(it), rz);
-    atomicAdd(scal + 1, rr);
-  }
+  const double v[2] = {block_sum(rz, red), block_sum(rr, red)};
+  double* const dst[2] = {scal + rz_new_slot(it), scal + 1};
+  ordered_accumulate<2>(v, dst, rb);
 }
 
 __global__ void __launch_bounds__(256) pcg_update_p_kernel(int64_t n2, const double2* __restrict__ r, const double2* __restrict__ minv,
@@ -282,7 +307,7 @@ extern "C" int fem_pcg_init(int64_t n, const double* rhs, const double* Kx0, con
   FEM_REQUIRE(rhs && minv && r && p && scal && n > 0, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   FEM_CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
-  pcg_init_kernel<<<vec_grid(n, sm_count_now()), 256, 0, st>>>(n, rhs, Kx0, free_mask, minv, r, p, scal);
+  pcg_init_kernel<<<vec_grid(n, sm_count_now()), 256, 0, st>>>(n, rhs, Kx0, free_mask, minv, r, p, scal, fem_red_buffer_for(scal, st));
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -300,7 +325,7 @@ extern "C" int fem_pcg_update_xr(int64_t n, const double* p, const double* q, co
   FEM_REQUIRE(p && q && minv && x && r && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
   pcg_update_xr_kernel<<<vec_grid(n / 2, sm_count_now()), 256, 0, (cudaStream_t)stream>>>(
       n / 2, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q), reinterpret_cast<const double2*>(minv),
-      reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), scal, iter);
+      reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), scal, iter, fem_red_buffer_for(scal, (cudaStream_t)stream));
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

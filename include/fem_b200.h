@@ -125,7 +125,11 @@ int fem_jacobi_setup(const fem_plan* plan, const double* K_vals, const uint8_t* 
                      fem_stream stream);
 /* PCG building blocks (device-resident scalars; used directly by the multi-GPU driver, which inserts
  * the halo exchange and the NCCL all-reduces between them).  scal is a device double[8]:
- * scal[0]=rz (even iterations), scal[1]=r'r, scal[2]=rz (odd iterations), scal[3]=p'Kp, scal[4]=|b|^2. */
+ * scal[0]=rz (even iterations), scal[1]=r'r, scal[2]=rz (odd iterations), scal[3]=p'Kp, scal[4]=|b|^2.
+ * The sums are order-deterministic (block sums added in a fixed order by the last block to finish, not atomically): the
+ * same inputs give the same bits.  The library keeps one 196 KB partial-sum buffer per distinct scal pointer (created by
+ * the first call, which must not be inside a stream capture) and one per plan for the SpMV's x'y: run at most one
+ * solve per scal array, and one dot-product SpMV per plan, at a time. */
 int fem_pcg_init(int64_t n, const double* rhs, const double* Kx0, const uint8_t* free_mask, const double* minv,
                  double* r, double* p, double* scal, fem_stream stream);
 int fem_pcg_spmv_dot(const fem_plan* plan, const double* K_vals, const double* p, double* q,
