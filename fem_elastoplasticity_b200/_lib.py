@@ -65,7 +65,7 @@ SIGNATURES = {
     "fem_tl_apply": [_i64, _i32, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp],
     "fem_mg_sizeof": [_i32],
     "fem_mg_lattice": [_i64, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
-    "fem_mg_galerkin_fine": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "fem_mg_galerkin_fine": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
     "fem_mg_galerkin_stencil": [_i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "fem_mg_block_jacobi": [_vp, _vp, _vp, _vp, _vp],
     "fem_mg_level_finalize": [_i64, _vp, _dbl, _vp, _vp],

@@ -55,48 +55,57 @@ __device__ __forceinline__ void parents(int ix, int jg, int (&I)[2], int (&J)[2]
   wy[1] = (jg & 1) ? 0.5 : 0.0;
 }
 
-// ---- A_1 = P^T K P from the block-CSR matrix: scatter of every 2x2 block of the rows in row_mask (FP64 atomics, set-up) ----
-__global__ void mg_galerkin_fine_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
-                                        const double* __restrict__ vals, const uint8_t* __restrict__ rmask, const uint8_t* __restrict__ cmask,
-                                        const int32_t* __restrict__ node_lat, int LX, int g0, Geom c, double* S, int32_t* err) {
-  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_n; a += (int64_t)gridDim.x * blockDim.x) {
-    const double mi0 = rmask ? (double)(rmask[2 * a] != 0) : 1.0, mi1 = rmask ? (double)(rmask[2 * a + 1] != 0) : 1.0;
-    if (mi0 == 0.0 && mi1 == 0.0) continue;
-    const int la = node_lat[a];
-    int Ia[2], Ja[2], Ib[2], Jb[2];
-    double wxa[2], wya[2], wxb[2], wyb[2];
-    parents(la % LX, la / LX + g0, Ia, Ja, wxa, wya);
-    const int p0 = nbr_ptr[a], deg = nbr_ptr[a + 1] - p0;
-    const double* row0 = vals + 4 * (int64_t)p0;
-    const double* row1 = row0 + 2 * deg;
-    for (int j = 0; j < deg; ++j) {
-      const int b = nbr_idx[p0 + j];
-      const int lb = node_lat[b];
-      parents(lb % LX, lb / LX + g0, Ib, Jb, wxb, wyb);
-      const double mj0 = cmask ? (double)(cmask[2 * b] != 0) : 1.0, mj1 = cmask ? (double)(cmask[2 * b + 1] != 0) : 1.0;
-      const double k[4] = {row0[2 * j] * mi0 * mj0, row0[2 * j + 1] * mi0 * mj1, row1[2 * j] * mi1 * mj0, row1[2 * j + 1] * mi1 * mj1};
-      if (k[0] == 0.0 && k[1] == 0.0 && k[2] == 0.0 && k[3] == 0.0) continue;
-      for (int ya = 0; ya < 2; ++ya)
-        for (int xa = 0; xa < 2; ++xa) {
-          const double wa = wxa[xa] * wya[ya];
-          if (wa == 0.0) continue;
-          const int jl = Ja[ya] - c.g0;
-          if (jl < 0 || jl >= c.nrows || Ia[xa] >= c.nxn) { atomicOr(err, 4); continue; }
-          const int64_t cn = Ia[xa] + (int64_t)jl * c.nxn;
-          for (int yb = 0; yb < 2; ++yb)
-            for (int xb = 0; xb < 2; ++xb) {
-              const double w = wa * wxb[xb] * wyb[yb];
-              if (w == 0.0) continue;
-              const int dx = Ib[xb] - Ia[xa], dy = Jb[yb] - Ja[ya];
-              if (dx < -1 || dx > 1 || dy < -1 || dy > 1) { atomicOr(err, 8); continue; }  // mesh edge longer than one lattice step
-              const int s = (dy + 1) * 3 + dx + 1;
+// ---- A_1 = P^T K P from the block-CSR matrix: one thread per level-1 node gathers its nine 2x2 blocks from the matrix rows of
+// the <= 9 fine nodes it interpolates to (weights 1, 1/2, 1/4), rows in row_mask x columns in col_mask, in a fixed order: no
+// atomics, so the hierarchy - and with it every multigrid solve - is reproducible bit for bit (a scatter with FP64 atomics
+// was not).  A fine row is read by up to four coarse nodes; set-up only. ----
+__global__ void __launch_bounds__(128) mg_galerkin_fine_kernel(const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
+                                                               const double* __restrict__ vals, const uint8_t* __restrict__ rmask,
+                                                               const uint8_t* __restrict__ cmask, const int32_t* __restrict__ lat, int lat_rows,
+                                                               const int32_t* __restrict__ node_lat, int LX, int g0, Geom c, double* __restrict__ S,
+                                                               int32_t* err) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c.n) return;
+  const int I = (int)(t % c.nxn), Jg = (int)(t / c.nxn) + c.g0;
+  double acc[9][4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (k[q] != 0.0) atomicAdd(S + (int64_t)(4 * s + q) * c.n + cn, w * k[q]);
-            }
-        }
+  for (int s = 0; s < 9; ++s) acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = 0.0;
+  for (int oy = -1; oy <= 1; ++oy)
+    for (int ox = -1; ox <= 1; ++ox) {
+      const int ix = 2 * I + ox, jl = 2 * Jg + oy - g0;  // fine lattice point: column, local row
+      if (ix < 0 || ix >= LX || jl < 0 || jl >= lat_rows) continue;
+      const int a = lat[(int64_t)jl * LX + ix];
+      if (a < 0) continue;
+      const double mi0 = rmask ? (double)(rmask[2 * (int64_t)a] != 0) : 1.0, mi1 = rmask ? (double)(rmask[2 * (int64_t)a + 1] != 0) : 1.0;
+      if (mi0 == 0.0 && mi1 == 0.0) continue;
+      const double wa = (ox ? 0.5 : 1.0) * (oy ? 0.5 : 1.0);
+      const int p0 = nbr_ptr[a], deg = nbr_ptr[a + 1] - p0;
+      const double* row0 = vals + 4 * (int64_t)p0;
+      const double* row1 = row0 + 2 * deg;
+      for (int j = 0; j < deg; ++j) {
+        const int b = nbr_idx[p0 + j];
+        const int lb = node_lat[b];
+        int Ib[2], Jb[2];
+        double wxb[2], wyb[2];
+        parents(lb % LX, lb / LX + g0, Ib, Jb, wxb, wyb);
+        const double mj0 = cmask ? (double)(cmask[2 * (int64_t)b] != 0) : 1.0, mj1 = cmask ? (double)(cmask[2 * (int64_t)b + 1] != 0) : 1.0;
+        const double k[4] = {row0[2 * j] * mi0 * mj0, row0[2 * j + 1] * mi0 * mj1, row1[2 * j] * mi1 * mj0, row1[2 * j + 1] * mi1 * mj1};
+        if (k[0] == 0.0 && k[1] == 0.0 && k[2] == 0.0 && k[3] == 0.0) continue;
+        for (int yb = 0; yb < 2; ++yb)
+          for (int xb = 0; xb < 2; ++xb) {
+            const double w = wa * wxb[xb] * wyb[yb];
+            if (w == 0.0) continue;
+            const int dx = Ib[xb] - I, dy = Jb[yb] - Jg;
+            if (dx < -1 || dx > 1 || dy < -1 || dy > 1) { atomicOr(err, 8); continue; }  // mesh edge longer than one lattice step
+            const int s = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[s][q] += w * k[q];
+          }
+      }
     }
-  }
+  for (int s = 0; s < 9; ++s)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) S[(int64_t)(4 * s + q) * c.n + t] = acc[s][q];
 }
 
 // ---- A_{l+1} = P^T A_l P between structured levels: one thread per coarse node gathers its 9 blocks (fully unrolled: the
@@ -361,25 +370,27 @@ template <int GROUP, int MODE, class VT>
 __global__ void __launch_bounds__(FEM_SPMV_THREADS) mg_fine_tiles_kernel(int64_t n_n, int64_t n_tiles, const int32_t* __restrict__ nbr_ptr,
                                                                          const int32_t* __restrict__ nbr_idx, const uint16_t* __restrict__ nbr_loc,
                                                                          const int32_t* __restrict__ tile_seg, const VT* __restrict__ vals,
-                                                                         const double* x, const MgFineEpilogue<MODE> epi, double* dot_out) {
+                                                                         const double* x, const MgFineEpilogue<MODE> epi, double* dot_out, const FemRedBuf rb) {
   __shared__ double red[32];
   __shared__ SpmvTileSmem sm;
   double dot = spmv_tiles_epi<GROUP, false, MgFineEpilogue<MODE>, VT>(n_n, n_tiles, nbr_ptr, nbr_idx, nbr_loc, tile_seg, vals, x, epi, sm);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
 template <int GROUP, int MODE, class VT>
 __global__ void __launch_bounds__(256) mg_fine_rows_kernel(int64_t n_n, const int32_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr_idx,
                                                            const VT* __restrict__ vals, const double* __restrict__ x,
-                                                           const MgFineEpilogue<MODE> epi, double* dot_out) {
+                                                           const MgFineEpilogue<MODE> epi, double* dot_out, const FemRedBuf rb) {
   __shared__ double red[32];
   double dot = spmv_rows_epi<GROUP, 2, MgFineEpilogue<MODE>, VT>(n_n, nbr_ptr, nbr_idx, vals, x, epi);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
@@ -427,13 +438,14 @@ struct MgStreamEpilogue {
 
 template <int GROUP, int MODE, class VT>
 __global__ void __launch_bounds__(FEM_STREAM_THREADS, 1) mg_fine_stream_kernel(const SpmvStreamArgs A, const VT* __restrict__ vals, const double* x,
-                                                                           const MgStreamEpilogue<MODE> epi, double* dot_out) {
+                                                                           const MgStreamEpilogue<MODE> epi, double* dot_out, const FemRedBuf rb) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   __shared__ double red[32];
   double dot = spmv_stream<GROUP, false, VT>(A, vals, x, epi, stream_smem);
   if (dot_out) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(dot_out, dot);
+    const double v[1] = {block_sum(dot, red)};
+    double* const dst[1] = {dot_out};
+    ordered_accumulate<1>(v, dst, rb);
   }
 }
 
@@ -582,7 +594,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(double* vals, int n
 
 // ---- CG steps around the V-cycle --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mg_pcg_init_kernel(int64_t n, const double* __restrict__ rhs, const uint8_t* __restrict__ mask,
-                                                          double* __restrict__ r, double* __restrict__ x, double* scal) {
+                                                          double* __restrict__ r, double* __restrict__ x, double* scal, const FemRedBuf rb) {
   __shared__ double red[32];
   double rr = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -592,14 +604,13 @@ __global__ void __launch_bounds__(256) mg_pcg_init_kernel(int64_t n, const doubl
     rr = fma(ri, ri, rr);
   }
   rr = block_sum(rr, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(scal + 1, rr);
-    atomicAdd(scal + 4, rr);
-  }
+  const double v[2] = {rr, rr};
+  double* const dst[2] = {scal + 1, scal + 4};
+  ordered_accumulate<2>(v, dst, rb);
 }
 
 __global__ void __launch_bounds__(256) mg_pcg_update_xr_kernel(int64_t n2, const double2* __restrict__ p, const double2* __restrict__ q,
-                                                               double2* __restrict__ x, double2* __restrict__ r, double* scal, int it) {
+                                                               double2* __restrict__ x, double2* __restrict__ r, double* scal, int it, const FemRedBuf rb) {
   __shared__ double red[32];
   const double rz_old = scal[(it & 1) ? 2 : 0], pq = scal[3];
   const double alpha = (pq != 0.0) ? rz_old / pq : 0.0;
@@ -615,8 +626,9 @@ __global__ void __launch_bounds__(256) mg_pcg_update_xr_kernel(int64_t n2, const
     r[i] = ri;
     rr = fma(ri.x, ri.x, fma(ri.y, ri.y, rr));
   }
-  rr = block_sum(rr, red);
-  if (threadIdx.x == 0) atomicAdd(scal + 1, rr);
+  const double v[1] = {block_sum(rr, red)};
+  double* const dst[1] = {scal + 1};
+  ordered_accumulate<1>(v, dst, rb);
 }
 
 __global__ void __launch_bounds__(256) mg_pcg_update_p_kernel(int64_t n2, const double2* __restrict__ z, double2* __restrict__ p, double* scal, int it) {
@@ -697,6 +709,7 @@ int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const d
                            D->own_node_lo, D->own_node_hi, 0, P->n_n};
   const SpmvShape sh = spmv_shape(P);
   epi.group = sh.group;
+  const FemRedBuf rb{P->red_partials, P->red_ticket};  // order-deterministic r'z of the last post-smoothing step
   const bool aligned = ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                          reinterpret_cast<uintptr_t>(D->dinv) | reinterpret_cast<uintptr_t>(D->d) | reinterpret_cast<uintptr_t>(D->mask)) & 15u) == 0;
   // default: every operand streamed through shared memory by a producer warp (FP32 values: three stages, 0.352 ms per
@@ -715,7 +728,7 @@ int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const d
       FEM_CUDA_CHECK(cudaFuncSetAttribute(mg_fine_stream_kernel<G, MODE, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
-    mg_fine_stream_kernel<G, MODE, VT><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K, x, se, dot);                               \
+    mg_fine_stream_kernel<G, MODE, VT><<<sb, FEM_STREAM_THREADS, smem, st>>>(A, K, x, se, dot, rb);                           \
   } while (0)
     if (sh.group == 4) MGS(4);
     else if (sh.group == 8) MGS(8);
@@ -726,13 +739,13 @@ int launch_fine_vt(const fem_plan* P, const fem_mg_desc* D, const VT* K, const d
   }
   if (spmv_use_tiles(P)) {
     const unsigned tb = spmv_tile_blocks(P);
-#define MGT(G) mg_fine_tiles_kernel<G, MODE, VT><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot)
+#define MGT(G) mg_fine_tiles_kernel<G, MODE, VT><<<tb, FEM_SPMV_THREADS, 0, st>>>(P->n_n, P->n_tiles, P->nbr_ptr, P->nbr_idx, P->nbr_loc, P->tile_seg, K, x, epi, dot, rb)
     if (sh.group == 4) MGT(4);
     else if (sh.group == 8) MGT(8);
     else MGT(16);
 #undef MGT
   } else {
-#define MGR(G) mg_fine_rows_kernel<G, MODE, VT><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K, x, epi, dot)
+#define MGR(G) mg_fine_rows_kernel<G, MODE, VT><<<sh.blocks, 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K, x, epi, dot, rb)
     if (sh.group == 4) MGR(4);
     else if (sh.group == 8) MGR(8);
     else MGR(16);
@@ -835,14 +848,13 @@ extern "C" int fem_mg_lattice(int64_t n_n, const double* coord, double x0, doubl
 }
 
 extern "C" int fem_mg_galerkin_fine(const fem_plan* P, const double* K_vals, const uint8_t* row_mask, const uint8_t* col_mask,
-                                    const int32_t* node_lat, int LX, int g0, int nxn, int nrows, int g0c, double* S, int32_t* err,
-                                    fem_stream stream) {
-  FEM_REQUIRE(P && K_vals && node_lat && S && err && LX > 0 && nxn > 0 && nrows > 0, "null pointer");
+                                    const int32_t* lat, int lat_rows, const int32_t* node_lat, int LX, int g0, int nxn, int nrows, int g0c,
+                                    double* S, int32_t* err, fem_stream stream) {
+  FEM_REQUIRE(P && K_vals && lat && node_lat && S && err && LX > 0 && lat_rows > 0 && nxn > 0 && nrows > 0, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const Geom c{nxn, nrows, g0c, 0, (int64_t)nxn * nrows};
-  FEM_CUDA_CHECK(cudaMemsetAsync(S, 0, sizeof(double) * 36 * (size_t)c.n, st));
-  mg_galerkin_fine_kernel<<<grid_for(P->n_n), 256, 0, st>>>(P->n_n, P->nbr_ptr, P->nbr_idx, K_vals, row_mask, col_mask ? col_mask : row_mask,
-                                                            node_lat, LX, g0, c, S, err);
+  mg_galerkin_fine_kernel<<<grid_for(c.n, 128), 128, 0, st>>>(P->nbr_ptr, P->nbr_idx, K_vals, row_mask, col_mask ? col_mask : row_mask, lat, lat_rows,
+                                                              node_lat, LX, g0, c, S, err);
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -984,7 +996,7 @@ extern "C" int fem_mg_pcg_init(int64_t n, const double* rhs, const uint8_t* mask
   FEM_REQUIRE(rhs && r && x && scal && n > 0, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   FEM_CUDA_CHECK(cudaMemsetAsync(scal, 0, 8 * sizeof(double), st));
-  mg_pcg_init_kernel<<<vgrid(n, 0), 256, 0, st>>>(n, rhs, mask, r, x, scal);
+  mg_pcg_init_kernel<<<vgrid(n, 0), 256, 0, st>>>(n, rhs, mask, r, x, scal, fem_red_buffer_for(scal, st));
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }
@@ -992,7 +1004,8 @@ extern "C" int fem_mg_pcg_init(int64_t n, const double* rhs, const uint8_t* mask
 extern "C" int fem_mg_pcg_update_xr(int64_t n, const double* p, const double* q, double* x, double* r, double* scal, int iter, fem_stream stream) {
   FEM_REQUIRE(p && q && x && r && scal && n > 0 && n % 2 == 0, "null pointer or odd n");
   mg_pcg_update_xr_kernel<<<vgrid(n / 2, 0), 256, 0, (cudaStream_t)stream>>>(n / 2, reinterpret_cast<const double2*>(p), reinterpret_cast<const double2*>(q),
-                                                                            reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), scal, iter);
+                                                                            reinterpret_cast<double2*>(x), reinterpret_cast<double2*>(r), scal, iter,
+                                                                            fem_red_buffer_for(scal, (cudaStream_t)stream));
   FEM_CUDA_CHECK(cudaGetLastError());
   return FEM_OK;
 }

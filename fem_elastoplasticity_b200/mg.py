@@ -346,8 +346,8 @@ class MultigridPCG:
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         # level 1 from the block-CSR matrix: rows of this rank's unknowns x all free columns
         l1 = self.lv[0]
-        call("fem_mg_galerkin_fine", P._h, _ptr(k_vals), _ptr(self.mask), _ptr(self.free_mask), _ptr(self.node_lat), LX, self.g0,
-             l1["nxn"], l1["nrows"], l1["g0"], _ptr(l1["S"]), _ptr(err), _stream())
+        call("fem_mg_galerkin_fine", P._h, _ptr(k_vals), _ptr(self.mask), _ptr(self.free_mask), _ptr(self.lat), self.lat_rows, _ptr(self.node_lat),
+             LX, self.g0, l1["nxn"], l1["nrows"], l1["g0"], _ptr(l1["S"]), _ptr(err), _stream())
         if int(err.item()) != 0:
             raise MultigridUnsupported(f"mesh edges do not fit the 9-point coarse stencil (code {int(err.item())})")
         if self.part is not None:

@@ -262,8 +262,8 @@ int fem_mg_sizeof(int which); /* sizeof fem_mg_exchange (0), fem_mg_level (1), f
 int fem_mg_lattice(int64_t n_n, const double* coord, double x0, double y0, double hx, double hy, int LX, int lat_rows, int g0,
                    int32_t* lat, int32_t* node_lat, int32_t* err, fem_stream stream);
 int fem_mg_galerkin_fine(const fem_plan* plan, const double* K_vals, const uint8_t* row_mask, const uint8_t* col_mask,
-                         const int32_t* node_lat, int LX, int g0, int nxn, int nrows, int g0c, double* S, int32_t* err,
-                         fem_stream stream);
+                         const int32_t* lat, int lat_rows, const int32_t* node_lat, int LX, int g0, int nxn, int nrows, int g0c,
+                         double* S, int32_t* err, fem_stream stream); /* gather per level-1 node, no atomics: reproducible */
 int fem_mg_galerkin_stencil(int nxf, int nrows_f, int g0f, int nrows_global_f, const double* Sf, int nxc, int nrows_c, int g0c,
                             int row_lo, int row_hi, double* Sc, fem_stream stream);
 int fem_mg_level_finalize(int64_t n, double* S, double thresh, double* dinv, fem_stream stream);

@@ -186,3 +186,28 @@ def test_fine_step_code_paths_agree(fem):
         assert float((outs[0][2] - r_ref).abs().max()) <= tol * float(r_ref.abs().max())
         assert float((outs[0][1] - d_ref).abs().max()) <= tol * float(d_ref.abs().max())
         assert float((outs[0][0] - (x + d_ref)).abs().max()) <= tol * float((x + d_ref).abs().max())
+
+
+def test_multigrid_solve_is_bit_reproducible(fem):
+    """No atomics on floating-point data anywhere in the multigrid CG: the level-1 Galerkin product is a gather, the transfers
+    are gathers, and every dot product adds its block sums in a fixed order.  Two independent set-ups + solves (graph replay and
+    eager launches) give the same hierarchy and the same solution bit for bit."""
+    torch, mg = fem["torch"], fem["mg"]
+    from fem_elastoplasticity_b200.plan import dp_return_map
+    d1, d2, wf = p1_tables()
+    m = fem["meshgen"].square_mesh_p1(257, 190, 10.0, 7.0)
+    P = fem["plan"].FemPlan(m["elements"], m["coordinates"], d1, d2, wf)
+    G, Kb, eta, c = fem["meshgen"].footing_materials(P.n_int)
+    k_el = P.assemble_elastic(G, Kb)
+    r = dp_return_map(fem["meshgen"].synthetic_strain(P.n_int), None, G, Kb, eta, c)
+    k_tan, F = P.assemble_tangent_force(r["ds"], r["s"])
+    mask = P.mask_u8(m["Q"])
+    runs = []
+    for use_graph in (True, False, True):
+        M = mg.MultigridPCG(P, mask, use_graph=use_graph).setup(k_el)
+        x, n_it, rel = M.solve(k_tan, -F, rtol=1e-10)
+        runs.append((x.clone(), n_it, rel, [lv["S"].clone() for lv in M.lv], M.lmax0))
+    for other in runs[1:]:
+        assert other[1] == runs[0][1] and other[2] == runs[0][2] and other[4] == runs[0][4]
+        assert all(torch.equal(a, b) for a, b in zip(runs[0][3], other[3]))
+        assert torch.equal(runs[0][0], other[0])
