@@ -21,10 +21,16 @@ k_el = P.assemble_elastic(G, Kb)
 r = dp_return_map(meshgen.synthetic_strain_global(P.n_int, 0), None, G, Kb, eta, c)
 k_tan, F = P.assemble_tangent_force(r["ds"], r["s"])
 mask = P.mask_u8(m["Q"])
-M = mg.MultigridPCG(P, mask).setup(k_el)
+M0 = mg.MultigridPCG(P, mask).setup(k_el)
 for rnd in range(2):
     for setting in [a for a in sys.argv[1:] if "=" in a]:
         key, val = setting.split("=")
+        if key.startswith("ctor:"):                      # constructor argument of MultigridPCG, e.g. ctor:max_coarse_dofs=4500
+            M = mg.MultigridPCG(P, mask, **{key[5:]: int(val)}).setup(k_el)
+            key = "mg_stencil_sym"
+            val = 0
+        else:
+            M = M0
         _lib.call("fem_set_tuning", key.encode(), int(val))
         M._graph = None
         x, its, rel = M.solve(k_tan, -F, rtol=1e-10)
