@@ -61,9 +61,13 @@ def _dev_f64(x, device, shape=None):
     else:
         a = np.ascontiguousarray(x, dtype=np.float64)
         h = torch.as_tensor(a)
+        t = None
         if a.nbytes >= _UPLOAD_MIN_BYTES and not h.is_pinned():
-            t = _upload_pageable(a, torch.device(device))
-        else:
+            try:
+                t = _upload_pageable(a, torch.device(device))
+            except RuntimeError:               # no page-locked staging memory on this host: ordinary upload
+                t = None
+        if t is None:
             t = h.to(device)
     t = t.contiguous()
     if shape is not None:

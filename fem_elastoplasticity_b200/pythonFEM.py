@@ -90,7 +90,10 @@ def _to_numpy(t):
     s -> internal_force) the upload does too - the CUDA runtime recognises page-locked source memory by address."""
     if t.numel() * t.element_size() < _PIN_MIN_BYTES:
         return t.cpu().numpy()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    try:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:                       # no page-locked memory left on this host: ordinary download
+        return t.cpu().numpy()
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return h.numpy()
