@@ -65,6 +65,17 @@ def chebyshev_coefficients(lmax, ratio, degree):
     return c1, c2
 
 
+def check_schedule(hint, check_every):
+    """First iteration at which a solve looks at its residual, given the iteration count ``hint`` of the previous solve with
+    the same tolerance (None: no previous solve): four iterations before it, rounded down to a multiple of ``check_every``."""
+    return 0 if hint is None else max(0, ((hint - 4) // check_every) * check_every)
+
+
+def next_check(it, n_it, check_every, skip_until):
+    """Iteration index of the next convergence check after iteration ``it``."""
+    return min(n_it, max((it // check_every + 1) * check_every, skip_until))
+
+
 def level_layouts(LX, NY, owned, max_coarse_dofs=2500, min_owned_rows=3, max_levels=MAX_LEVELS, replicate_below=600000):
     """Layouts of the structured levels l = 1 .. L over an LX x NY node lattice whose rows are owned by the ranks as the
     half-open global ranges ``owned`` (one per rank, ascending, covering [0, NY)).
@@ -569,8 +580,15 @@ class MultigridPCG:
                 self._capture_pair(k_vals)
             graph = self._graph
         self.launches_last = 0
+        # Convergence checks cost a host round trip during which the GPU idles (and a MAX-reduction of the error word across the
+        # ranks).  Successive solves of a Newton loop take almost the same number of iterations, so the checks start four
+        # iterations before the count of the previous solve on this object; the stopping rule itself is unchanged (the first
+        # check that finds rel <= rtol ends the solve - a solve that converges much faster than its predecessor runs a few
+        # iterations more than it needed).
+        hint = getattr(self, "_hint_iters", {}).get(rtol)              # per tolerance: a looser solve says nothing about a tighter one
+        skip_until = 0 if iters is not None else check_schedule(hint, check_every)
         while it < n_it:
-            nxt = n_it if iters is not None else min(n_it, (it // check_every + 1) * check_every)
+            nxt = n_it if iters is not None else next_check(it, n_it, check_every, skip_until)
             while it < nxt:
                 if graph is not None and it % 2 == 0 and it + 2 <= nxt:
                     graph.replay()
@@ -591,6 +609,8 @@ class MultigridPCG:
         if iters is None and not rel <= rtol:
             from .distributed import PCGNotConverged
             raise PCGNotConverged("multigrid PCG", it, rel, rtol)
+        if iters is None:
+            self.__dict__.setdefault("_hint_iters", {})[rtol] = it
         return self.x, it, rel
 
     def _capture_pair(self, k_vals):

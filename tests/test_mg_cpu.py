@@ -6,7 +6,7 @@ import scipy.sparse as sp
 
 from oracle import fem_oracle as fo
 from mg_reference import ReferenceMG, prolongation
-from fem_elastoplasticity_b200.mg import chebyshev_coefficients, level_layouts
+from fem_elastoplasticity_b200.mg import check_schedule, chebyshev_coefficients, level_layouts, next_check
 
 
 def strip_owned(ny_cells, world):
@@ -112,3 +112,29 @@ def test_prolongation_reproduces_linear_fields():
     xf, yf = np.meshgrid(np.arange(9) * 1.0, np.arange(6) * 1.0)
     ff = np.stack([(1 + 2 * xf + 3 * yf).ravel(), (xf - yf).ravel()], axis=1).ravel()
     np.testing.assert_allclose(P @ fc, ff, atol=1e-12)
+
+
+def test_convergence_check_schedule():
+    """Checks start four iterations before the previous solve's count; the stopping rule (first check with rel <= rtol) is kept."""
+    def run(n_conv, hint, check_every=2, maxit=500, start=0):
+        it, checks, skip = start, [], check_schedule(hint, check_every)
+        while it < maxit:
+            it = next_check(it, maxit, check_every, skip)
+            checks.append(it)
+            if it >= n_conv:
+                break
+        return it, checks
+    assert run(28, None) == (28, list(range(2, 29, 2)))
+    assert run(28, 28) == (28, [24, 26, 28]) and run(27, 28) == (28, [24, 26, 28])
+    assert run(12, 28) == (24, [24])                      # much faster than its predecessor: a few iterations too many
+    assert run(40, 28)[1][:2] == [24, 26] and run(40, 28)[0] == 40
+    assert run(3, 3) == (4, [2, 4]) and run(28, 28, start=2)[1] == [24, 26, 28]   # start=2: the two eager iterations before the graph
+    assert run(30, 28, check_every=3) == (30, [24, 27, 30]) and run(5, 2, maxit=4) == (4, [2, 4])
+    for hint in (None, 0, 1, 5, 28, 499):
+        for ce in (1, 2, 3, 7):
+            it, last = 0, -1
+            skip = check_schedule(hint, ce)
+            while it < 50:
+                it = next_check(it, 50, ce, skip)
+                assert it > last and it <= 50
+                last = it
